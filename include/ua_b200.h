@@ -1,0 +1,153 @@
+/*
+ * ua_b200.h — C ABI of libua_b200.so, the sm_100a implementation of the Uni-Adapter
+ * per-sample test-time hot path (point tokenizer, zero-shot head, DOTA / MODE-DOTA cache step).
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the library never allocates, never synchronises and never copies to the host: the caller owns
+ *     every buffer (including scratch) and the stream;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - return value: UA_OK (0) or a negative UA_ERR_* code; ua_last_error() gives a message;
+ *   - all tensors are dense row-major fp32 unless the parameter says otherwise.
+ *
+ * Each entry point cites the reference interface (file:line under the reference repo) it replaces.
+ */
+#ifndef UA_B200_H
+#define UA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UA_OK 0
+#define UA_ERR_INVALID_ARG (-1)
+#define UA_ERR_UNSUPPORTED (-2)
+#define UA_ERR_CUDA (-3)
+
+#define UA_ABI_VERSION 1
+
+/* Library identity / diagnostics ------------------------------------------------------------ */
+int ua_abi_version(void);
+const char* ua_last_error(void);
+/* Number of kernel launches issued by this library since load (or since ua_reset_launch_count). */
+int64_t ua_launch_count(void);
+void ua_reset_launch_count(void);
+/* Tuning knobs for experiments: "fps_threads", "knn_warps", "modedota_threads" (0 = built-in heuristic). */
+int ua_set_tuning(const char* key, int value);
+
+/* ------------------------------------------------------------------------------------------
+ * Tokenizer
+ * ---------------------------------------------------------------------------------------- */
+
+/* Farthest-point sampling, one cloud per thread block, running-min distances in registers.
+ * Replaces: models/ulip/pointbert/misc.py:40-60 fps(xyz,npoint)            (random start, returns points)
+ *           models/openshape/pointnet_util.py:64-86 farthest_point_sample  (random start, returns idx)
+ *           models/point_encoder.py:7-14 fps() -> pointnet2_ops.furthest_point_sample + gather_operation
+ *                                                                           (start index 0)
+ * Arithmetic: dist = ((dx*dx)+(dy*dy))+(dz*dz), every operation rounded separately (no FMA),
+ * running min initialised to 1e10, argmax takes the FIRST maximal index.
+ *   xyz        [B,N,3] f32
+ *   start_idx  [B] i64, or NULL for start index 0 in every cloud
+ *   skip_small_norm  != 0: points with x*x+y*y+z*z <= 1e-3 are never selected/updated (pointnet2_ops quirk)
+ *   out_idx    [B,G] i32 or i64 (idx_is_i64), may be NULL
+ *   out_centers[B,G,3] f32, may be NULL
+ *   scratch    [B,N] f32, only required when N > UA_FPS_MAX_REG_POINTS (else may be NULL)
+ */
+#define UA_FPS_MAX_REG_POINTS 16384
+int ua_fps_f32(const float* xyz, int B, int N, int G, const int64_t* start_idx, int skip_small_norm,
+               void* out_idx, int idx_is_i64, float* out_centers, float* scratch, void* stream);
+
+/* kNN grouping fused with gather + centre subtraction + channel concat; the (G,N) distance matrix is
+ * never materialised.
+ * Replaces: models/point_encoder.py:17-49,99-127 (knn_point/square_distance/Group.forward, Uni3D)
+ *           models/ulip/pointbert/dvae.py:116-181 (same, ULIP: no colour)
+ * Ranking value: d = ((-2*fma(cz,pz,fma(cy,py,cx*px))) + ((cx*cx+cy*cy)+cz*cz)) + ((px*px+py*py)+pz*pz)
+ * (the reference's expanded form, fp32); the k smallest (d, index) pairs in lexicographic order are kept,
+ * i.e. ties go to the lower point index. Neighbours are emitted nearest-first.
+ *   xyz      [B,N,3]      rgb [B,N,3] or NULL      centers [B,G,3]
+ *   out_idx  [B,G,k] i32/i64 or NULL
+ *   out_neigh[B,G,k,3] (xyz - centre) or NULL
+ *   out_feat [B,G,k,6] (xyz - centre, rgb) or NULL (requires rgb)
+ *   1 <= k <= 128, k <= N
+ */
+int ua_knn_group_f32(const float* xyz, const float* rgb, const float* centers, int B, int N, int G, int k,
+                     void* out_idx, int idx_is_i64, float* out_neigh, float* out_feat, void* stream);
+
+/* Ball-query grouping (first `nsample` points, in index order, with d <= radius2; padded with the first hit).
+ * Replaces: models/openshape/pointnet_util.py:89-146 (query_ball_point + sample_and_group).
+ * A point is REJECTED iff d > radius2 with d computed as in ua_knn_group_f32.
+ *   feat [B,N,C] or NULL (C == 0)
+ *   out_idx [B,S,nsample] i32/i64 or NULL
+ *   out_new_points [B,S,nsample,3+C] = (xyz - centre, feat) or NULL
+ * A centre with no point inside the ball (impossible when centres are cloud points) yields index N-1
+ * clamped gathers; the reference raises an index error there.
+ */
+int ua_ball_group_f32(const float* xyz, const float* feat, int C, const float* centers, int B, int N, int S,
+                      float radius2, int nsample, void* out_idx, int idx_is_i64, float* out_new_points,
+                      void* stream);
+
+/* out[b,c,g] = in[b,c,idx[b,g]] — pointnet2_ops.gather_operation (models/point_encoder.py:13). */
+int ua_gather_points_f32(const float* in, const int32_t* idx, int B, int C, int N, int G, float* out,
+                         void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Zero-shot cosine-logit head
+ * Replaces: Uni_Adapter.py:21-26,53-75 (softmax_entropy, get_logits_wrapper after the encoder)
+ *   x [B,D] raw encoder output; text [K,D] unit-norm rows (clip_weights = text^T)
+ *   out_xnorm [B,D] = x/||x||; out_logits [B,K] = (scale*xnorm) @ text^T ; out_prob = softmax(logits);
+ *   out_entropy [B] = -sum p*log(p+1e-10); out_argmax [B] i32 (first maximal index).
+ * Any out_* except out_logits may be NULL.
+ * ---------------------------------------------------------------------------------------- */
+int ua_head_f32(const float* x, int B, int D, const float* text, int K, float scale, float* out_xnorm,
+                float* out_logits, float* out_prob, float* out_entropy, int32_t* out_argmax, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * MODE-DOTA (diagonal Gaussian mixture cache)
+ * Replaces: dota_mixture.py:117-156 (_get_var/_log_likelihood), :162-234 (fit), :236-267 (predict).
+ * State of S independent streams: mu,var [S,K,M,D]; pi,c [S,K,M]; class_counts [S,K] (S = 1 for the
+ * reference's single adapter object; S > 1 runs S adapters in lock-step in one launch).
+ * One launch evaluates  predict(x_pred) on the CURRENT state (if x_pred != NULL) and then applies
+ * fit(x_fit, gamma_class) in place (if x_fit != NULL); each class's (M,D) state tile is read from HBM once
+ * and written once (TMA bulk copies through a two-stage shared-memory ring).
+ *   x_pred [S,Bp,D] -> out_logits [S,Bp,ldo] written at columns [k_out_offset, k_out_offset+K)
+ *   x_fit [S,B,D], gamma_class [S,B,ldg] read at columns [k_gamma_offset, k_gamma_offset+K)
+ * (the offsets / leading dimensions let a class-sharded rank use the full-width logits / prob_map buffers).
+ * Limits: M <= 16, Bp + B <= 160, 2*M*D*4 bytes + 27 KB <= 227 KB.
+ * ---------------------------------------------------------------------------------------- */
+int ua_modedota_step_f32(const float* x_pred, int Bp, const float* x_fit, const float* gamma_class, int B,
+                         int ldg, int k_gamma_offset, float* mu, float* var, float* pi, float* c,
+                         float* class_counts, int S, int K, int M, int D, float eps, float* out_logits, int ldo,
+                         int k_out_offset, void* stream);
+
+/* Fusion of zero-shot and cache logits, Uni_Adapter.py:491-521 (MODE-DOTA, mode=1) or
+ * dota_mixture.py:289-293 (DOTA, mode=0: final = clip + w*dota).
+ *   w = min(rho * mean(c) / batch, eta) computed on device from c[count_c]
+ *   (c_sum_override >= 0 replaces sum(c): used by class-sharded ranks, closed form K + fits*B)
+ *   dota_logits may be fp16 (dota_is_f16) as DOTA.predict returns half.
+ *   out_final [R,K], out_argmax [R] i32, out_scaled_dota [R,K] or NULL
+ */
+int ua_fuse_logits_f32(const float* clip_logits, const void* dota_logits, int dota_is_f16, int R, int K,
+                       const float* c, int count_c, float c_sum_override, float c_count_total, float rho,
+                       float eta, float batch, int mode, float* out_final, int32_t* out_argmax,
+                       float* out_scaled_dota, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * DOTA (full covariance)
+ * Replaces: dota.py:41-63 (fit), :72-87 (predict). dota.py:66-69 (update: DxD inverse) stays a library call.
+ *   fit:  mu [K,D], c [K], Sigma [K,D,D], overall [D,D] updated in place from x [B,D], y [B,K].
+ *   predict: x_h [R,D] f16, Lambda_h [D,D] f16, mu [K,D] f32 -> out_scores_h [R,K] f16, rounding to fp16
+ *            at the reference's rounding points (M, W, M*W, 0.5*sum, X@W, difference).
+ * ---------------------------------------------------------------------------------------- */
+int ua_dota_fit_f32(const float* x, const float* y, int B, float* mu, float* c, float* Sigma, float* overall,
+                    int K, int D, void* stream);
+int ua_dota_predict_f16(const void* x_h, int R, const void* Lambda_h, const float* mu, int K, int D,
+                        void* out_scores_h, void* stream);
+/* A = (1-eps)*overall + eps*I  (the matrix dota.py:67-68 inverts), written to out [D,D]. */
+int ua_dota_regularize_f32(const float* overall, int D, float eps, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UA_B200_H */

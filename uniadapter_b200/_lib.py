@@ -1,0 +1,106 @@
+"""ctypes binding of libua_b200.so (the C ABI declared in include/ua_b200.h).
+
+The shared library is built in-tree by ``uniadapter_b200/csrc/Makefile`` (nvcc, sm_100a only). There is no CPU
+fallback: every op of this package calls through this module and raises if the library is missing or a call
+returns an error code.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libua_b200.so")
+CSRC_DIR = os.path.join(_HERE, "csrc")
+
+UA_OK = 0
+_lib = None
+
+_P = C.c_void_p
+_I = C.c_int
+_F = C.c_float
+
+# name -> (restype, argtypes); mirrors include/ua_b200.h one to one
+SIGNATURES = {
+    "ua_abi_version": (_I, []),
+    "ua_last_error": (C.c_char_p, []),
+    "ua_launch_count": (C.c_int64, []),
+    "ua_reset_launch_count": (None, []),
+    "ua_set_tuning": (_I, [C.c_char_p, _I]),
+    "ua_fps_f32": (_I, [_P, _I, _I, _I, _P, _I, _P, _I, _P, _P, _P]),
+    "ua_knn_group_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _I, _P, _P, _P]),
+    "ua_ball_group_f32": (_I, [_P, _P, _I, _P, _I, _I, _I, _F, _I, _P, _I, _P, _P]),
+    "ua_gather_points_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
+    "ua_head_f32": (_I, [_P, _I, _I, _P, _I, _F, _P, _P, _P, _P, _P, _P]),
+    "ua_modedota_step_f32": (_I, [_P, _I, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _I, _I, _P]),
+    "ua_fuse_logits_f32": (_I, [_P, _P, _I, _I, _I, _P, _I, _F, _F, _F, _F, _F, _I, _P, _P, _P, _P]),
+    "ua_dota_fit_f32": (_I, [_P, _P, _I, _P, _P, _P, _P, _I, _I, _P]),
+    "ua_dota_predict_f16": (_I, [_P, _I, _P, _P, _I, _I, _P, _P]),
+    "ua_dota_regularize_f32": (_I, [_P, _I, _F, _P, _P]),
+}
+
+
+class UaError(RuntimeError):
+    pass
+
+
+def build(verbose: bool = False) -> str:
+    """Compile libua_b200.so in-tree (nvcc cross-compiles for sm_100a without a GPU)."""
+    proc = subprocess.run(["make", "-C", CSRC_DIR, "-j8"], capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise UaError("building libua_b200.so failed:\n" + proc.stdout[-4000:] + proc.stderr[-4000:])
+    if verbose:
+        print(proc.stdout[-2000:])
+    return LIB_PATH
+
+
+def lib() -> C.CDLL:
+    """The loaded library. Fails loudly when it has not been built: no other implementation exists."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise UaError(
+                f"{LIB_PATH} is missing: build it with `make -C {CSRC_DIR}` (or __graft_entry__.build()). "
+                "uniadapter_b200 has no CPU or PyTorch fallback.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def ptr(t: torch.Tensor | None):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise UaError("uniadapter_b200 kernels need CUDA tensors (no CPU fallback)")
+    if not t.is_contiguous():
+        raise UaError("uniadapter_b200 kernels need contiguous tensors")
+    return t.data_ptr()
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def check(rc: int, what: str) -> None:
+    if rc != UA_OK:
+        raise UaError(f"{what} failed with code {rc}: {lib().ua_last_error().decode()}")
+
+
+def launch_count() -> int:
+    return int(lib().ua_launch_count())
+
+
+def reset_launch_count() -> None:
+    lib().ua_reset_launch_count()
+
+
+def set_tuning(key: str, value: int) -> None:
+    check(lib().ua_set_tuning(key.encode(), int(value)), "ua_set_tuning")

@@ -1,0 +1,49 @@
+// Host-side plumbing of libua_b200.so: error string, launch counter, tuning knobs.
+#include <stdarg.h>
+#include <string.h>
+#include <atomic>
+#include "common.cuh"
+
+namespace ua {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+extern int g_fps_threads;
+extern int g_knn_warps;
+extern int g_modedota_threads;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+int check_launch(const char* what) {
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+    return UA_ERR_CUDA;
+  }
+  return UA_OK;
+}
+
+}  // namespace ua
+
+extern "C" int ua_abi_version(void) { return UA_ABI_VERSION; }
+extern "C" const char* ua_last_error(void) { return ua::g_err; }
+extern "C" int64_t ua_launch_count(void) { return ua::g_launches.load(); }
+extern "C" void ua_reset_launch_count(void) { ua::g_launches.store(0); }
+
+extern "C" int ua_set_tuning(const char* key, int value) {
+  if (!key) return UA_ERR_INVALID_ARG;
+  if (!strcmp(key, "fps_threads")) { ua::g_fps_threads = value; return UA_OK; }
+  if (!strcmp(key, "knn_warps")) { ua::g_knn_warps = value; return UA_OK; }
+  if (!strcmp(key, "modedota_threads")) { ua::g_modedota_threads = value; return UA_OK; }
+  ua::set_error("ua_set_tuning: unknown key '%s'", key);
+  return UA_ERR_INVALID_ARG;
+}

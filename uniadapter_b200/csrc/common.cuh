@@ -1,0 +1,130 @@
+// Shared helpers for the sm_100a kernels of libua_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/ua_b200.h"
+
+namespace ua {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+constexpr unsigned kFullMask = 0xffffffffu;
+
+// ---- error plumbing (host) -------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);  // counts one launch, returns UA_OK / UA_ERR_CUDA
+void count_launch();
+
+#define UA_REQUIRE(cond, ...)            \
+  do {                                   \
+    if (!(cond)) {                       \
+      ua::set_error(__VA_ARGS__);        \
+      return UA_ERR_INVALID_ARG;         \
+    }                                    \
+  } while (0)
+
+#define UA_UNSUPPORTED(cond, ...)        \
+  do {                                   \
+    if (cond) {                          \
+      ua::set_error(__VA_ARGS__);        \
+      return UA_ERR_UNSUPPORTED;         \
+    }                                    \
+  } while (0)
+
+// ---- device helpers --------------------------------------------------------------------------
+
+// Squared distance exactly as torch.sum((p - c) ** 2, -1) evaluates it on three channels:
+// every subtraction, square and addition rounded separately, summed left to right.
+__device__ __forceinline__ float sqdist_nofma(float px, float py, float pz, float cx, float cy, float cz) {
+  const float dx = __fsub_rn(px, cx), dy = __fsub_rn(py, cy), dz = __fsub_rn(pz, cz);
+  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// sum(p ** 2, -1) on three channels, no FMA.
+__device__ __forceinline__ float sqnorm_nofma(float x, float y, float z) {
+  return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+}
+
+// The reference's expanded squared distance (square_distance): ((-2 * <c,p>) + |c|^2) + |p|^2 with the
+// K=3 inner product evaluated as fma(c2,p2, fma(c1,p1, c0*p0)).
+__device__ __forceinline__ float expanded_sqdist(float cx, float cy, float cz, float cn, float px, float py,
+                                                 float pz, float pn) {
+  const float dot = __fmaf_rn(cz, pz, __fmaf_rn(cy, py, __fmul_rn(cx, px)));
+  return __fadd_rn(__fadd_rn(__fmul_rn(-2.0f, dot), cn), pn);
+}
+
+// Order-preserving map float -> uint32 (total order, -0 < +0).
+__device__ __forceinline__ uint32_t float_to_ordered(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFullMask, v, o));
+  return v;
+}
+
+// ---- bulk async copy (TMA unit, 1-D) + mbarrier ----------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t phase) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(phase)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  while (!mbar_try_wait(bar, phase)) {
+  }
+}
+// global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// shared -> global bulk copy (bulk async-group completion).
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
+               "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
+}  // namespace ua

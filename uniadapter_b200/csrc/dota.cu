@@ -1,0 +1,201 @@
+// DOTA (full-covariance) cache kernels for sm_100a. Replaces dota.py:41-63 (fit) and :72-87 (predict);
+// dota.py:66-69 (update) keeps its library inverse, fed by ua_dota_regularize_f32.
+//
+// fit is a pure HBM stream over Sigma [K,D,D] (read + write once, 8*K*D^2 bytes): each thread owns one float4 of a
+// (row, 4 columns) position and walks the K classes, applying the rank-B update and accumulating the class mean
+// (overall_Sigma) on the fly, so neither delta (K,D,D) nor a second pass for the mean ever touch memory.
+#include "common.cuh"
+
+namespace ua {
+namespace {
+
+constexpr int kTileRows = 8;     // rows of Sigma per CTA
+constexpr int kTileCols = 128;   // columns per CTA (32 threads x float4)
+
+// grid: (ceil(D/128), ceil(D/8)); block: (32, 8)
+__global__ void __launch_bounds__(256)
+    dota_sigma_kernel(const float* __restrict__ x, const float* __restrict__ y, int B, const float* __restrict__ mu,
+                      const float* __restrict__ c, float* __restrict__ Sigma, float* __restrict__ overall, int K,
+                      int D) {
+  const int j = blockIdx.x * kTileCols + threadIdx.x * 4;
+  const int i = blockIdx.y * kTileRows + threadIdx.y;
+  if (i >= D || j >= D) return;
+  float4 mean = make_float4(0.f, 0.f, 0.f, 0.f);
+  const size_t DD = (size_t)D * D;
+  float* sp = Sigma + (size_t)i * D + j;
+#pragma unroll 4
+  for (int k = 0; k < K; ++k) {
+    const float4 sg = *reinterpret_cast<const float4*>(sp + (size_t)k * DD);
+    const float mi = __ldg(mu + (size_t)k * D + i);
+    const float4 mj = __ldg(reinterpret_cast<const float4*>(mu + (size_t)k * D + j));
+    const float ck = __ldg(c + k);
+    float4 delta;
+    float sw;
+    {
+      const float y0 = __ldg(y + k);
+      const float xi = __fsub_rn(__ldg(x + i), mi);
+      const float4 xj = __ldg(reinterpret_cast<const float4*>(x + j));
+      const float wi = __fmul_rn(y0, xi);
+      delta.x = __fmul_rn(wi, __fsub_rn(xj.x, mj.x));
+      delta.y = __fmul_rn(wi, __fsub_rn(xj.y, mj.y));
+      delta.z = __fmul_rn(wi, __fsub_rn(xj.z, mj.z));
+      delta.w = __fmul_rn(wi, __fsub_rn(xj.w, mj.w));
+      sw = y0;
+    }
+    for (int b = 1; b < B; ++b) {
+      const float yb = __ldg(y + (size_t)b * K + k);
+      const float xi = __fsub_rn(__ldg(x + (size_t)b * D + i), mi);
+      const float4 xj = __ldg(reinterpret_cast<const float4*>(x + (size_t)b * D + j));
+      const float wi = __fmul_rn(yb, xi);
+      delta.x = __fmaf_rn(wi, __fsub_rn(xj.x, mj.x), delta.x);
+      delta.y = __fmaf_rn(wi, __fsub_rn(xj.y, mj.y), delta.y);
+      delta.z = __fmaf_rn(wi, __fsub_rn(xj.z, mj.z), delta.z);
+      delta.w = __fmaf_rn(wi, __fsub_rn(xj.w, mj.w), delta.w);
+      sw = __fadd_rn(sw, yb);
+    }
+    const float denom = __fadd_rn(ck, sw);
+    float4 out;
+    out.x = __fdiv_rn(__fadd_rn(__fmul_rn(ck, sg.x), delta.x), denom);
+    out.y = __fdiv_rn(__fadd_rn(__fmul_rn(ck, sg.y), delta.y), denom);
+    out.z = __fdiv_rn(__fadd_rn(__fmul_rn(ck, sg.z), delta.z), denom);
+    out.w = __fdiv_rn(__fadd_rn(__fmul_rn(ck, sg.w), delta.w), denom);
+    *reinterpret_cast<float4*>(sp + (size_t)k * DD) = out;
+    mean.x += out.x, mean.y += out.y, mean.z += out.z, mean.w += out.w;
+  }
+  const float kf = (float)K;
+  float4 m4 = make_float4(__fdiv_rn(mean.x, kf), __fdiv_rn(mean.y, kf), __fdiv_rn(mean.z, kf), __fdiv_rn(mean.w, kf));
+  *reinterpret_cast<float4*>(overall + (size_t)i * D + j) = m4;
+}
+
+// mu' = (y^T x + c*mu) / (s + c), c' = c + s   (run after the Sigma kernel, which needs the old mu and c)
+__global__ void __launch_bounds__(256)
+    dota_mean_kernel(const float* __restrict__ x, const float* __restrict__ y, int B, float* __restrict__ mu,
+                     float* __restrict__ c, int K, int D) {
+  const int k = blockIdx.x;
+  float sw = __ldg(y + k);
+  for (int b = 1; b < B; ++b) sw = __fadd_rn(sw, __ldg(y + (size_t)b * K + k));
+  const float ck = c[k];
+  const float denom = __fadd_rn(sw, ck);
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float wx = __fmul_rn(__ldg(y + k), __ldg(x + d));
+    for (int b = 1; b < B; ++b) wx = __fmaf_rn(__ldg(y + (size_t)b * K + k), __ldg(x + (size_t)b * D + d), wx);
+    const float m = mu[(size_t)k * D + d];
+    mu[(size_t)k * D + d] = __fdiv_rn(__fadd_rn(wx, __fmul_rn(ck, m)), denom);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) c[k] = __fadd_rn(ck, sw);
+}
+
+// One CTA per class k. W[:,k] = Lambda @ M[:,k] (fp32 accumulate, rounded to fp16), then the discriminant in
+// fp16 arithmetic with the reference's rounding points.
+__global__ void __launch_bounds__(512)
+    dota_predict_kernel(const __half* __restrict__ xh, int R, const __half* __restrict__ lam,
+                        const float* __restrict__ mu, int K, int D, __half* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  float* s_m = reinterpret_cast<float*>(s_raw);  // [D] fp16-rounded class mean (as float)
+  float* s_w = s_m + D;                          // [D] fp16-rounded W column (as float)
+  __shared__ float s_part[16];
+  __shared__ float s_c;
+  const int k = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
+  for (int d = tid; d < D; d += blockDim.x) s_m[d] = __half2float(__float2half_rn(__ldg(mu + (size_t)k * D + d)));
+  __syncthreads();
+  for (int i = warp; i < D; i += W) {
+    const __half* lrow = lam + (size_t)i * D;
+    float acc = 0.f;
+    if ((D & 7) == 0) {
+      for (int jj = lane * 8; jj < D; jj += 256) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(lrow + jj));
+        const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = __half22float2(h2[q]);
+          acc = fmaf(f.x, s_m[jj + 2 * q], acc);
+          acc = fmaf(f.y, s_m[jj + 2 * q + 1], acc);
+        }
+      }
+    } else {
+      for (int jj = lane; jj < D; jj += 32) acc = fmaf(__half2float(lrow[jj]), s_m[jj], acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) s_w[i] = __half2float(__float2half_rn(acc));
+  }
+  __syncthreads();
+  // c = 0.5 * sum_i half(M_i * W_i)   (sum accumulated in fp32, rounded to half, then halved in half)
+  float part = 0.f;
+  for (int i = tid; i < D; i += blockDim.x) part += __half2float(__float2half_rn(s_m[i] * s_w[i]));
+  part = warp_sum(part);
+  if (lane == 0) s_part[warp] = part;
+  __syncthreads();
+  if (tid == 0) {
+    float t = 0.f;
+    for (int w = 0; w < W; ++w) t += s_part[w];
+    const float sum_h = __half2float(__float2half_rn(t));
+    s_c = __half2float(__float2half_rn(0.5f * sum_h));
+  }
+  __syncthreads();
+  for (int r = 0; r < R; ++r) {
+    float dot = 0.f;
+    for (int i = tid; i < D; i += blockDim.x) dot = fmaf(__half2float(xh[(size_t)r * D + i]), s_w[i], dot);
+    dot = warp_sum(dot);
+    __syncthreads();
+    if (lane == 0) s_part[warp] = dot;
+    __syncthreads();
+    if (tid == 0) {
+      float t = 0.f;
+      for (int w = 0; w < W; ++w) t += s_part[w];
+      const float s_h = __half2float(__float2half_rn(t));
+      out[(size_t)r * K + k] = __float2half_rn(s_h - s_c);
+    }
+  }
+}
+
+__global__ void dota_regularize_kernel(const float* __restrict__ overall, int D, float one_minus_eps, float eps,
+                                       float* __restrict__ out) {
+  const size_t n = (size_t)D * D;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(t / D), j = (int)(t - (size_t)i * D);
+    out[t] = __fadd_rn(__fmul_rn(one_minus_eps, overall[t]), i == j ? eps : 0.f);
+  }
+}
+
+}  // namespace
+}  // namespace ua
+
+extern "C" int ua_dota_fit_f32(const float* x, const float* y, int B, float* mu, float* c, float* Sigma,
+                               float* overall, int K, int D, void* stream) {
+  using namespace ua;
+  UA_REQUIRE(x && y && mu && c && Sigma && overall, "ua_dota_fit_f32: NULL pointer");
+  UA_REQUIRE(B >= 1 && K >= 1 && D >= 1, "ua_dota_fit_f32: bad sizes B=%d K=%d D=%d", B, K, D);
+  UA_UNSUPPORTED((D & 3) != 0, "ua_dota_fit_f32: D=%d must be a multiple of 4", D);
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((D + kTileCols - 1) / kTileCols, (D + kTileRows - 1) / kTileRows), block(32, kTileRows);
+  dota_sigma_kernel<<<grid, block, 0, st>>>(x, y, B, mu, c, Sigma, overall, K, D);
+  int rc = check_launch("ua_dota_fit_f32(sigma)");
+  if (rc != UA_OK) return rc;
+  dota_mean_kernel<<<K, 256, 0, st>>>(x, y, B, mu, c, K, D);
+  return check_launch("ua_dota_fit_f32(mean)");
+}
+
+extern "C" int ua_dota_predict_f16(const void* x_h, int R, const void* Lambda_h, const float* mu, int K, int D,
+                                   void* out_scores_h, void* stream) {
+  using namespace ua;
+  UA_REQUIRE(x_h && Lambda_h && mu && out_scores_h, "ua_dota_predict_f16: NULL pointer");
+  UA_REQUIRE(R >= 1 && K >= 1 && D >= 1, "ua_dota_predict_f16: bad sizes R=%d K=%d D=%d", R, K, D);
+  const size_t smem = (size_t)2 * D * sizeof(float);
+  UA_UNSUPPORTED(smem > 200 * 1024, "ua_dota_predict_f16: D=%d too large", D);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(dota_predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dota_predict_kernel<<<K, 512, smem, (cudaStream_t)stream>>>((const __half*)x_h, R, (const __half*)Lambda_h, mu, K, D,
+                                                            (__half*)out_scores_h);
+  return check_launch("ua_dota_predict_f16");
+}
+
+extern "C" int ua_dota_regularize_f32(const float* overall, int D, float eps, float* out, void* stream) {
+  using namespace ua;
+  UA_REQUIRE(overall && out && D >= 1, "ua_dota_regularize_f32: bad arguments");
+  const float one_minus = (float)(1.0 - (double)eps);
+  const size_t n = (size_t)D * D;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  dota_regularize_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(overall, D, one_minus, eps, out);
+  return check_launch("ua_dota_regularize_f32");
+}

@@ -1,0 +1,214 @@
+// Farthest-point sampling for sm_100a: one cloud per CTA, the cloud's running-min distances and coordinates
+// live in registers for the whole G-iteration loop; each iteration costs one block barrier and four REDUX
+// warp reductions (max of the distance bits, then min index among the maxima).
+//
+// Semantics follow models/ulip/pointbert/misc.py:40-60 and models/openshape/pointnet_util.py:64-86 of the
+// reference: dist = sum((xyz - centroid)**2, -1) rounded per operation, distance = min(distance, dist) from an
+// initial 1e10, farthest = first index of the maximum. The Uni3D path (models/point_encoder.py:7-14, un-vendored
+// pointnet2_ops CUDA) maps to start index 0 (+ optional skip of near-origin points).
+#include "common.cuh"
+
+namespace ua {
+
+int g_fps_threads = 0;  // tuning override (0 = heuristic)
+
+namespace {
+
+constexpr float kFpsInit = 1e10f;
+
+__device__ __forceinline__ void block_argmax(uint32_t bits, uint32_t idx, uint2 (*s_red)[32], int buf, int lane,
+                                             int warp, int nwarps, uint32_t& out_idx) {
+  // warp level: maximum of the (non-negative) float bit patterns, lowest index among the maxima
+  const uint32_t wmax = __reduce_max_sync(kFullMask, bits);
+  const uint32_t widx = __reduce_min_sync(kFullMask, bits == wmax ? idx : 0xffffffffu);
+  if (lane == 0) s_red[buf][warp] = make_uint2(wmax, widx);
+  __syncthreads();
+  const uint2 v = lane < nwarps ? s_red[buf][lane] : make_uint2(0u, 0xffffffffu);
+  const uint32_t bmax = __reduce_max_sync(kFullMask, v.x);
+  out_idx = __reduce_min_sync(kFullMask, v.x == bmax ? v.y : 0xffffffffu);
+}
+
+template <typename IdxT>
+__device__ __forceinline__ void write_selection(const int* s_sel, const float* cloud_smem, const float* cloud_gmem,
+                                                int b, int G, IdxT* out_idx, float* out_centers) {
+  __syncthreads();
+  for (int i = threadIdx.x; i < G; i += blockDim.x) {
+    const int p = s_sel[i];
+    if (out_idx) out_idx[(size_t)b * G + i] = (IdxT)p;
+  }
+  if (out_centers) {
+    for (int i = threadIdx.x; i < 3 * G; i += blockDim.x) {
+      const int p = s_sel[i / 3];
+      const int ch = i - 3 * (i / 3);
+      out_centers[(size_t)b * G * 3 + i] = cloud_smem ? cloud_smem[3 * p + ch] : cloud_gmem[3 * (size_t)p + ch];
+    }
+  }
+}
+
+// Register-resident path: N <= PPT * blockDim.x, cloud also staged in shared memory for the centroid fetch.
+template <int PPT, typename IdxT>
+__global__ void __launch_bounds__(PPT == 12 ? 896 : 1024, 1)
+    fps_reg_kernel(const float* __restrict__ xyz, int N, int G, const long long* __restrict__ start_idx,
+                   int skip_small, IdxT* __restrict__ out_idx, float* __restrict__ out_centers) {
+  extern __shared__ __align__(16) float s_dyn[];
+  float* s_xyz = s_dyn;                              // [3N]
+  int* s_sel = reinterpret_cast<int*>(s_dyn + 3 * N);  // [G]
+  __shared__ uint2 s_red[2][32];
+
+  const int b = blockIdx.x;
+  const int T = blockDim.x;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+  const float* cloud = xyz + (size_t)b * N * 3;
+
+  for (int i = tid; i < 3 * N; i += T) s_xyz[i] = __ldg(cloud + i);
+  __syncthreads();
+
+  float px[PPT], py[PPT], pz[PPT], dmin[PPT];
+#pragma unroll
+  for (int j = 0; j < PPT; ++j) {
+    const int p = j * T + tid;
+    bool valid = p < N;
+    px[j] = valid ? s_xyz[3 * p + 0] : 0.f;
+    py[j] = valid ? s_xyz[3 * p + 1] : 0.f;
+    pz[j] = valid ? s_xyz[3 * p + 2] : 0.f;
+    if (skip_small && valid) valid = sqnorm_nofma(px[j], py[j], pz[j]) > 1e-3f;
+    // an excluded slot keeps distance 0 forever: it can only tie with exhausted points, and then loses on index
+    dmin[j] = valid ? kFpsInit : 0.f;
+  }
+
+  long long s0 = start_idx ? start_idx[b] : 0;
+  if (s0 < 0) s0 = 0;
+  if (s0 >= N) s0 = N - 1;
+  uint32_t cur = (uint32_t)s0;
+
+  for (int i = 0; i < G; ++i) {
+    if (tid == 0) s_sel[i] = (int)cur;
+    if (i == G - 1) break;
+    const float cx = s_xyz[3 * cur + 0], cy = s_xyz[3 * cur + 1], cz = s_xyz[3 * cur + 2];
+    float best = -1.f;
+    int bestj = 0;
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+      const float d = sqdist_nofma(px[j], py[j], pz[j], cx, cy, cz);
+      const float dm = fminf(dmin[j], d);
+      dmin[j] = dm;
+      if (dm > best) {
+        best = dm;
+        bestj = j;
+      }
+    }
+    block_argmax(__float_as_uint(best), (uint32_t)(bestj * T + tid), s_red, i & 1, lane, warp, nwarps, cur);
+  }
+  write_selection<IdxT>(s_sel, s_xyz, nullptr, b, G, out_idx, out_centers);
+}
+
+// Large-cloud path (N > 16384): distances in a caller-provided [B,N] scratch, coordinates re-read through L2.
+template <typename IdxT>
+__global__ void __launch_bounds__(1024, 1)
+    fps_gmem_kernel(const float* __restrict__ xyz, int N, int G, const long long* __restrict__ start_idx,
+                    int skip_small, IdxT* __restrict__ out_idx, float* __restrict__ out_centers,
+                    float* __restrict__ scratch) {
+  extern __shared__ __align__(16) float s_dyn[];
+  int* s_sel = reinterpret_cast<int*>(s_dyn);  // [G]
+  __shared__ uint2 s_red[2][32];
+  const int b = blockIdx.x, T = blockDim.x, tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+  const float* cloud = xyz + (size_t)b * N * 3;
+  float* dist = scratch + (size_t)b * N;
+  for (int p = tid; p < N; p += T) {
+    bool valid = true;
+    if (skip_small) valid = sqnorm_nofma(cloud[3 * p], cloud[3 * p + 1], cloud[3 * p + 2]) > 1e-3f;
+    dist[p] = valid ? kFpsInit : 0.f;
+  }
+  long long s0 = start_idx ? start_idx[b] : 0;
+  if (s0 < 0) s0 = 0;
+  if (s0 >= N) s0 = N - 1;
+  uint32_t cur = (uint32_t)s0;
+  for (int i = 0; i < G; ++i) {
+    if (tid == 0) s_sel[i] = (int)cur;
+    if (i == G - 1) break;
+    const float cx = __ldg(cloud + 3 * (size_t)cur), cy = __ldg(cloud + 3 * (size_t)cur + 1),
+                cz = __ldg(cloud + 3 * (size_t)cur + 2);
+    float best = -1.f;
+    uint32_t besti = 0;
+    for (int p = tid; p < N; p += T) {  // each thread owns a fixed set of p: no cross-thread hazard on dist[]
+      const float d = sqdist_nofma(__ldg(cloud + 3 * (size_t)p), __ldg(cloud + 3 * (size_t)p + 1),
+                                   __ldg(cloud + 3 * (size_t)p + 2), cx, cy, cz);
+      const float dm = fminf(dist[p], d);
+      dist[p] = dm;
+      if (dm > best) {
+        best = dm;
+        besti = (uint32_t)p;
+      }
+    }
+    block_argmax(__float_as_uint(best), besti, s_red, i & 1, lane, warp, nwarps, cur);
+  }
+  write_selection<IdxT>(s_sel, nullptr, cloud, b, G, out_idx, out_centers);
+}
+
+template <int PPT, typename IdxT>
+int launch_reg(const float* xyz, int B, int N, int G, const int64_t* start_idx, int skip_small, void* out_idx,
+               float* out_centers, int threads, cudaStream_t st) {
+  const size_t smem = (size_t)3 * N * sizeof(float) + (size_t)G * sizeof(int);
+  auto kern = fps_reg_kernel<PPT, IdxT>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("ua_fps_f32: cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
+      return UA_ERR_CUDA;
+    }
+  }
+  kern<<<B, threads, smem, st>>>(xyz, N, G, (const long long*)start_idx, skip_small, (IdxT*)out_idx, out_centers);
+  return check_launch("ua_fps_f32");
+}
+
+template <typename IdxT>
+int dispatch(const float* xyz, int B, int N, int G, const int64_t* start_idx, int skip_small, void* out_idx,
+             float* out_centers, float* scratch, cudaStream_t st) {
+  if (N > UA_FPS_MAX_REG_POINTS) {
+    UA_REQUIRE(scratch != nullptr, "ua_fps_f32: N=%d > %d needs a [B,N] f32 scratch", N, UA_FPS_MAX_REG_POINTS);
+    UA_UNSUPPORTED(G > 40000, "ua_fps_f32: G=%d too large for the large-cloud path", G);
+    const size_t smem = (size_t)G * sizeof(int);
+    auto kern = fps_gmem_kernel<IdxT>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<B, 1024, smem, st>>>(xyz, N, G, (const long long*)start_idx, skip_small, (IdxT*)out_idx, out_centers,
+                                scratch);
+    return check_launch("ua_fps_f32(gmem)");
+  }
+  // threads per cloud: the loop is latency-bound for small clouds (few warps -> cheaper barrier) and
+  // issue-bound for large ones (N*12 instructions per iteration on one SM).
+  int target = g_fps_threads > 0 ? g_fps_threads : (N <= 2048 ? 256 : 1024);
+  static const int kPpt[] = {1, 2, 4, 8, 12, 16};
+  int ppt = 16;
+  for (int cand : kPpt) {
+    const int need = (N + cand - 1) / cand;
+    if (need <= target && need <= (cand == 12 ? 896 : 1024)) {
+      ppt = cand;
+      break;
+    }
+  }
+  int threads = (((N + ppt - 1) / ppt) + 31) / 32 * 32;
+  switch (ppt) {
+    case 1: return launch_reg<1, IdxT>(xyz, B, N, G, start_idx, skip_small, out_idx, out_centers, threads, st);
+    case 2: return launch_reg<2, IdxT>(xyz, B, N, G, start_idx, skip_small, out_idx, out_centers, threads, st);
+    case 4: return launch_reg<4, IdxT>(xyz, B, N, G, start_idx, skip_small, out_idx, out_centers, threads, st);
+    case 8: return launch_reg<8, IdxT>(xyz, B, N, G, start_idx, skip_small, out_idx, out_centers, threads, st);
+    case 12: return launch_reg<12, IdxT>(xyz, B, N, G, start_idx, skip_small, out_idx, out_centers, threads, st);
+    default: return launch_reg<16, IdxT>(xyz, B, N, G, start_idx, skip_small, out_idx, out_centers, threads, st);
+  }
+}
+
+}  // namespace
+}  // namespace ua
+
+extern "C" int ua_fps_f32(const float* xyz, int B, int N, int G, const int64_t* start_idx, int skip_small_norm,
+                          void* out_idx, int idx_is_i64, float* out_centers, float* scratch, void* stream) {
+  using namespace ua;
+  UA_REQUIRE(xyz != nullptr, "ua_fps_f32: xyz is NULL");
+  UA_REQUIRE(B >= 0 && N >= 1 && G >= 1, "ua_fps_f32: bad sizes B=%d N=%d G=%d", B, N, G);
+  if (B == 0) return UA_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  return idx_is_i64 ? dispatch<long long>(xyz, B, N, G, start_idx, skip_small_norm, out_idx, out_centers, scratch, st)
+                    : dispatch<int>(xyz, B, N, G, start_idx, skip_small_norm, out_idx, out_centers, scratch, st);
+}

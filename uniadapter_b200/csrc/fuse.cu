@@ -1,0 +1,131 @@
+// Fusion of zero-shot logits with cache logits, one CTA per row.
+//   mode 1 (MODE-DOTA, Uni_Adapter.py:491-521): d = w*dota; entropy-weighted blend of clip and d, where the second
+//           weight is normalised with the ALREADY-normalised first weight (the reference's own arithmetic).
+//   mode 0 (DOTA, dota_mixture.py:289-293): final = clip + w*dota, the product taken in fp16 when dota is fp16
+//           (torch type promotion of a 0-dim fp32 tensor times a half tensor).
+//   w = min(rho * mean(c) / batch, eta)
+#include "common.cuh"
+
+namespace ua {
+namespace {
+
+__device__ __forceinline__ float block_sum(float v, float* s_tmp) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) s_tmp[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int w = 0; w < W; ++w) t += s_tmp[w];
+  return t;
+}
+
+__device__ __forceinline__ float block_max(float v, float* s_tmp) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) s_tmp[warp] = v;
+  __syncthreads();
+  float t = -INFINITY;
+  for (int w = 0; w < W; ++w) t = fmaxf(t, s_tmp[w]);
+  return t;
+}
+
+// -sum softmax(v) * log(softmax(v) + 1e-10) over K entries produced by `get(k)`
+template <typename F>
+__device__ __forceinline__ float softmax_entropy(F get, int K, float* s_tmp) {
+  float mx = -INFINITY;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) mx = fmaxf(mx, get(k));
+  mx = block_max(mx, s_tmp);
+  float se = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) se += expf(get(k) - mx);
+  se = block_sum(se, s_tmp);
+  float ent = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float p = __fdiv_rn(expf(get(k) - mx), se);
+    ent += p * logf(p + 1e-10f);
+  }
+  return -block_sum(ent, s_tmp);
+}
+
+__global__ void __launch_bounds__(256)
+    fuse_kernel(const float* __restrict__ clip, const void* __restrict__ dota, int dota_is_f16, int K,
+                const float* __restrict__ c, int count_c, float c_sum_override, float c_count_total, float rho,
+                float eta, float batch, int mode, float* __restrict__ out_final, int* __restrict__ out_argmax,
+                float* __restrict__ out_scaled) {
+  __shared__ float s_tmp[8];
+  __shared__ float s_best[8];
+  __shared__ unsigned s_besti[8];
+  const int r = blockIdx.x;
+  const float* crow = clip + (size_t)r * K;
+  const float* drow32 = dota_is_f16 ? nullptr : reinterpret_cast<const float*>(dota) + (size_t)r * K;
+  const __half* drow16 = dota_is_f16 ? reinterpret_cast<const __half*>(dota) + (size_t)r * K : nullptr;
+
+  float csum = c_sum_override;
+  if (!(c_sum_override >= 0.f)) {
+    float part = 0.f;
+    for (int i = threadIdx.x; i < count_c; i += blockDim.x) part += __ldg(c + i);
+    csum = block_sum(part, s_tmp);
+  }
+  const float cmean = __fdiv_rn(csum, c_count_total);
+  const float w = fminf(__fdiv_rn(__fmul_rn(cmean, rho), batch), eta);
+
+  auto scaled = [&](int k) -> float {
+    if (dota_is_f16) {
+      const float wh = __half2float(__float2half_rn(w));
+      return __half2float(__float2half_rn(wh * __half2float(drow16[k])));
+    }
+    return __fmul_rn(w, drow32[k]);
+  };
+
+  float wc = 1.f, wd = 1.f;
+  if (mode == 1) {
+    const float hc = softmax_entropy([&](int k) { return crow[k]; }, K, s_tmp);
+    const float hd = softmax_entropy(scaled, K, s_tmp);
+    const float a = __fdiv_rn(1.f, __fadd_rn(hc, 1e-3f));
+    const float b = __fdiv_rn(1.f, __fadd_rn(hd, 1e-3f));
+    wc = __fdiv_rn(a, __fadd_rn(a, b));
+    wd = __fdiv_rn(b, __fadd_rn(wc, b));  // sic: normalised with the updated clip weight
+  }
+  float best = -INFINITY;
+  unsigned besti = 0xffffffffu;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float d = scaled(k);
+    const float f = mode == 1 ? __fadd_rn(__fmul_rn(wc, crow[k]), __fmul_rn(wd, d)) : __fadd_rn(crow[k], d);
+    out_final[(size_t)r * K + k] = f;
+    if (out_scaled) out_scaled[(size_t)r * K + k] = d;
+    if (f > best) best = f, besti = k;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+  const float wmx = warp_max(best);
+  const unsigned wmi = __reduce_min_sync(kFullMask, best == wmx ? besti : 0xffffffffu);
+  __syncthreads();
+  if (lane == 0) s_best[warp] = wmx, s_besti[warp] = wmi;
+  __syncthreads();
+  if (threadIdx.x == 0 && out_argmax) {
+    float m = s_best[0];
+    unsigned a = s_besti[0];
+    for (int q = 1; q < W; ++q)
+      if (s_best[q] > m || (s_best[q] == m && s_besti[q] < a)) m = s_best[q], a = s_besti[q];
+    out_argmax[r] = (int)a;
+  }
+}
+
+}  // namespace
+}  // namespace ua
+
+extern "C" int ua_fuse_logits_f32(const float* clip_logits, const void* dota_logits, int dota_is_f16, int R, int K,
+                                  const float* c, int count_c, float c_sum_override, float c_count_total, float rho,
+                                  float eta, float batch, int mode, float* out_final, int32_t* out_argmax,
+                                  float* out_scaled_dota, void* stream) {
+  using namespace ua;
+  UA_REQUIRE(clip_logits && dota_logits && out_final, "ua_fuse_logits_f32: NULL pointer");
+  UA_REQUIRE(R >= 1 && K >= 1, "ua_fuse_logits_f32: bad sizes R=%d K=%d", R, K);
+  UA_REQUIRE(c_sum_override >= 0.f || (c && count_c >= 1), "ua_fuse_logits_f32: need c[] or c_sum_override");
+  UA_REQUIRE(c_count_total > 0.f && batch > 0.f, "ua_fuse_logits_f32: c_count_total and batch must be > 0");
+  UA_REQUIRE(mode == 0 || mode == 1, "ua_fuse_logits_f32: mode must be 0 or 1");
+  fuse_kernel<<<R, 256, 0, (cudaStream_t)stream>>>(clip_logits, dota_logits, dota_is_f16, K, c, count_c,
+                                                   c_sum_override, c_count_total, rho, eta, batch, mode, out_final,
+                                                   out_argmax, out_scaled_dota);
+  return check_launch("ua_fuse_logits_f32");
+}

@@ -1,0 +1,77 @@
+"""DOTA: full-covariance online Gaussian discriminant cache. Mirrors the reference's ``DOTA`` (dota.py:19-87):
+same constructor, attributes (``mu, c, Sigma, overall_Sigma, Lambda, epsilon``) and methods (fit, update, predict).
+
+fit -> ua_dota_fit_f32 (one HBM pass over Sigma, class mean fused); predict -> ua_dota_predict_f16 (fp16 rounding
+points of the reference); update keeps the library inverse (torch.linalg.inv -> cuSOLVER), fed by
+ua_dota_regularize_f32 (SURVEY §8f-3 lists a custom SPD inverse as a later row).
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import _lib
+
+
+class DOTA(nn.Module):
+    def __init__(self, cfg, input_shape, num_classes, clip_weights, streaming_update_Sigma=True, prior_pre_steps=None,
+                 device=None):
+        super().__init__()
+        if device is None:
+            device = 'cuda'
+        self.device = torch.device(device)
+        self.input_shape = input_shape
+        self.num_classes = num_classes
+        if not streaming_update_Sigma:
+            raise NotImplementedError("streaming_update_Sigma=False is not part of the hot path")
+        self.streaming_update_Sigma = True
+        self.epsilon = cfg['epsilon']
+        self.mu = clip_weights.T.to(self.device).float().contiguous()
+        self.c = torch.ones(num_classes, dtype=torch.float32, device=self.device)
+        eye = torch.eye(input_shape, dtype=torch.float32, device=self.device)
+        self.Sigma = (cfg['sigma'] * eye).repeat(num_classes, 1, 1).contiguous()
+        self.overall_Sigma = torch.mean(self.Sigma, dim=0).contiguous()
+        # sigma*I is diagonal: its pseudo-inverse is the reciprocal diagonal (dota.py:31 uses pinverse in double)
+        self.Lambda = torch.linalg.pinv(self.overall_Sigma.double()).half().contiguous()
+        self._reg = torch.empty_like(self.overall_Sigma)
+        if prior_pre_steps is not None:
+            self.prior_pre_steps = prior_pre_steps
+            self.update_prior = True
+            self.cum_soft_labels = torch.zeros((1, num_classes), dtype=torch.float32, device=self.device)
+            self.prior_step = 0
+        else:
+            self.update_prior = False
+
+    @torch.no_grad()
+    def fit(self, x, y):
+        x = x.to(self.device).float().contiguous()
+        y = y.to(self.device).float().contiguous()
+        if self.update_prior:
+            self.cum_soft_labels = self.cum_soft_labels + y
+            self.prior_step = self.prior_step + 1
+        B = x.shape[0]
+        rc = _lib.lib().ua_dota_fit_f32(_lib.ptr(x), _lib.ptr(y), B, _lib.ptr(self.mu), _lib.ptr(self.c),
+                                        _lib.ptr(self.Sigma), _lib.ptr(self.overall_Sigma), self.num_classes,
+                                        self.input_shape, _lib.stream_ptr())
+        _lib.check(rc, "ua_dota_fit_f32")
+
+    @torch.no_grad()
+    def update(self):
+        rc = _lib.lib().ua_dota_regularize_f32(_lib.ptr(self.overall_Sigma), self.input_shape, float(self.epsilon),
+                                               _lib.ptr(self._reg), _lib.stream_ptr())
+        _lib.check(rc, "ua_dota_regularize_f32")
+        self.Lambda = torch.linalg.inv(self._reg).half().contiguous()
+
+    @torch.no_grad()
+    def predict(self, X):
+        X = X.to(self.device).half().contiguous()
+        R = X.shape[0]
+        out = torch.empty((R, self.num_classes), dtype=torch.float16, device=self.device)
+        rc = _lib.lib().ua_dota_predict_f16(_lib.ptr(X), R, _lib.ptr(self.Lambda), _lib.ptr(self.mu),
+                                            self.num_classes, self.input_shape, _lib.ptr(out), _lib.stream_ptr())
+        _lib.check(rc, "ua_dota_predict_f16")
+        if self.update_prior:
+            prior = self.cum_soft_labels + (self.prior_pre_steps / self.num_classes)
+            prior = prior / (self.prior_pre_steps + self.prior_step)
+            out = out + torch.log(prior + 1e-10)
+        return out

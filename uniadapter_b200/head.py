@@ -1,0 +1,70 @@
+"""Zero-shot cosine-logit head. Mirrors Uni_Adapter.py:21-26 (softmax_entropy) and :53-75 (get_logits_wrapper).
+
+Text features follow one convention everywhere: ``text`` is (K,D) row-major with unit-norm rows and
+``clip_weights = text.t()`` is the (D,K) matrix the reference multiplies with.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+
+def zero_shot_head(x: torch.Tensor, text: torch.Tensor, scale: float = 100.0, *, want_prob: bool = True):
+    """x (B,D) raw encoder output, text (K,D) -> (xnorm, logits, entropy, prob, argmax int32 (B,))."""
+    x = x.float().contiguous()
+    text = text.float().contiguous()
+    B, D = x.shape
+    K = text.shape[0]
+    if text.shape[1] != D:
+        raise ValueError(f"text features {tuple(text.shape)} do not match feature dim {D}")
+    dev = x.device
+    xnorm = torch.empty_like(x)
+    logits = torch.empty((B, K), dtype=torch.float32, device=dev)
+    prob = torch.empty((B, K), dtype=torch.float32, device=dev) if want_prob else None
+    entropy = torch.empty((B,), dtype=torch.float32, device=dev)
+    argmax = torch.empty((B,), dtype=torch.int32, device=dev)
+    rc = _lib.lib().ua_head_f32(_lib.ptr(x), B, D, _lib.ptr(text), K, float(scale), _lib.ptr(xnorm), _lib.ptr(logits),
+                                _lib.ptr(prob), _lib.ptr(entropy), _lib.ptr(argmax), _lib.stream_ptr())
+    _lib.check(rc, "ua_head_f32")
+    return xnorm, logits, entropy, prob, argmax
+
+
+def _as_text_rows(clip_weights: torch.Tensor, feat_dim: int) -> torch.Tensor:
+    """Accept the reference's (D,K) ``clip_weights`` (or a (K,D) text matrix) and return (K,D) rows."""
+    if clip_weights.shape[0] == feat_dim and clip_weights.shape[1] != feat_dim:
+        return clip_weights.t().contiguous()
+    if clip_weights.shape[1] == feat_dim and clip_weights.shape[0] != feat_dim:
+        return clip_weights.contiguous()
+    return clip_weights.t().contiguous()  # square: the reference convention is (D,K)
+
+
+def encode(args, model, feature: torch.Tensor) -> torch.Tensor:
+    """The encoder call of get_logits_wrapper (Uni_Adapter.py:54-66)."""
+    if args.vlm3d == 'uni3d':
+        return model.encode_pc(feature)
+    xyz = feature[:, :, :3]
+    if args.vlm3d == 'ulip':
+        return model(xyz)
+    if args.vlm3d == 'openshape':
+        return model(xyz, feature)
+    raise ValueError(f"unknown vlm3d {args.vlm3d!r}")
+
+
+def get_logits_wrapper(args, model, feature: torch.Tensor, clip_weights: torch.Tensor):
+    """Drop-in for Uni_Adapter.py:53-75: returns (pc_features, logits, loss, prob_map, pred).
+
+    ``pred`` is a Python int for batch 1 (as the reference, which only supports batch 1 here — SURVEY D7) and an
+    int32 tensor otherwise.
+    """
+    raw = encode(args, model, feature)
+    text = _as_text_rows(clip_weights, raw.shape[-1])
+    pc_features, logits, loss, prob_map, argmax = zero_shot_head(raw, text, 100.0)
+    pred = int(argmax[0]) if argmax.numel() == 1 else argmax
+    return pc_features, logits, loss, prob_map, pred
+
+
+def softmax_entropy(x: torch.Tensor, enable_softmax: bool = True, temperature: float = 1.0) -> torch.Tensor:
+    """Uni_Adapter.py:21-26 (host-side helper; the fused kernels compute the same quantity on device)."""
+    probs = torch.softmax(x / temperature, dim=1) if enable_softmax else x
+    return -(probs * torch.log(probs + 1e-10)).sum(dim=1)
