@@ -65,7 +65,8 @@ int ua_fps_f32(const float* xyz, int B, int N, int G, const int64_t* start_idx, 
  *           models/ulip/pointbert/dvae.py:116-181 (same, ULIP: no colour)
  * Ranking value: d = ((-2*fma(cz,pz,fma(cy,py,cx*px))) + ((cx*cx+cy*cy)+cz*cz)) + ((px*px+py*py)+pz*pz)
  * (the reference's expanded form, fp32); the k smallest (d, index) pairs in lexicographic order are kept,
- * i.e. ties go to the lower point index. Neighbours are emitted nearest-first.
+ * i.e. ties go to the lower point index. Neighbours are emitted in ascending point-index order (the reference's
+ * topk(sorted=False) order is unspecified; everything downstream is permutation-invariant over a group).
  *   xyz      [B,N,3]      rgb [B,N,3] or NULL      centers [B,G,3]
  *   out_idx  [B,G,k] i32/i64 or NULL
  *   out_neigh[B,G,k,3] (xyz - centre) or NULL
@@ -95,12 +96,14 @@ int ua_gather_points_f32(const float* in, const int32_t* idx, int B, int C, int 
 /* ------------------------------------------------------------------------------------------
  * Zero-shot cosine-logit head
  * Replaces: Uni_Adapter.py:21-26,53-75 (softmax_entropy, get_logits_wrapper after the encoder)
- *   x [B,D] raw encoder output; text [K,D] unit-norm rows (clip_weights = text^T)
+ *   x [B,D] raw encoder output; text [num_text,K,D] unit-norm rows (clip_weights = text^T). num_text = 1 is the
+ *   reference's single text matrix; num_text = S gives every block of B/S consecutive rows its own matrix
+ *   (independent streams whose text residuals are learned separately).
  *   out_xnorm [B,D] = x/||x||; out_logits [B,K] = (scale*xnorm) @ text^T ; out_prob = softmax(logits);
  *   out_entropy [B] = -sum p*log(p+1e-10); out_argmax [B] i32 (first maximal index).
- * Any out_* except out_logits may be NULL.
+ * out_prob / out_entropy / out_argmax may be NULL.
  * ---------------------------------------------------------------------------------------- */
-int ua_head_f32(const float* x, int B, int D, const float* text, int K, float scale, float* out_xnorm,
+int ua_head_f32(const float* x, int B, int D, const float* text, int num_text, int K, float scale, float* out_xnorm,
                 float* out_logits, float* out_prob, float* out_entropy, int32_t* out_argmax, void* stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -123,14 +126,15 @@ int ua_modedota_step_f32(const float* x_pred, int Bp, const float* x_fit, const 
 
 /* Fusion of zero-shot and cache logits, Uni_Adapter.py:491-521 (MODE-DOTA, mode=1) or
  * dota_mixture.py:289-293 (DOTA, mode=0: final = clip + w*dota).
- *   w = min(rho * mean(c) / batch, eta) computed on device from c[count_c]
+ *   w = min(rho * mean(c) / batch, eta) computed on device from c[count_c]; row r reads c + r*c_row_stride
+ *   (stride 0: one adapter for all rows; stride K*M: one adapter per row / stream)
  *   (c_sum_override >= 0 replaces sum(c): used by class-sharded ranks, closed form K + fits*B)
  *   dota_logits may be fp16 (dota_is_f16) as DOTA.predict returns half.
  *   out_final [R,K], out_argmax [R] i32, out_scaled_dota [R,K] or NULL
  */
 int ua_fuse_logits_f32(const float* clip_logits, const void* dota_logits, int dota_is_f16, int R, int K,
-                       const float* c, int count_c, float c_sum_override, float c_count_total, float rho,
-                       float eta, float batch, int mode, float* out_final, int32_t* out_argmax,
+                       const float* c, int count_c, int c_row_stride, float c_sum_override, float c_count_total,
+                       float rho, float eta, float batch, int mode, float* out_final, int32_t* out_argmax,
                        float* out_scaled_dota, void* stream);
 
 /* ------------------------------------------------------------------------------------------

@@ -134,11 +134,15 @@ def gather(xyz: np.ndarray, idx: np.ndarray) -> np.ndarray:
     return np.stack([xyz[b][idx[b]] for b in range(B)], axis=0)
 
 
-def group_knn(xyz: np.ndarray, npoint: int, k: int, rgb=None, start_idx=None, skip_small_norm=False, threads: int = 1):
-    """Group.forward (point_encoder.py:99-127 / dvae.py:159-181): returns dict(fps_idx, center, idx, neigh[, feat])."""
+def group_knn(xyz: np.ndarray, npoint: int, k: int, rgb=None, start_idx=None, skip_small_norm=False, threads: int = 1,
+              sort_by_index: bool = False):
+    """Group.forward (point_encoder.py:99-127 / dvae.py:159-181): returns dict(fps_idx, center, idx, neigh[, feat]).
+    Neighbours nearest-first, or in ascending point index (the CUDA kernel's emission order) if sort_by_index."""
     fidx = fps(xyz, npoint, start_idx, skip_small_norm, threads)
     center = gather(xyz, fidx)
     idx = knn(xyz, center, k, threads)
+    if sort_by_index:
+        idx = np.sort(idx, axis=-1)
     neigh = gather(xyz, idx) - center[:, :, None, :]
     out = dict(fps_idx=fidx, center=center, idx=idx, neigh=neigh.astype(np.float32))
     if rgb is not None:

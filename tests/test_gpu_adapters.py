@@ -1,0 +1,238 @@
+"""GPU: head, MODE-DOTA step, DOTA and fusion kernels against the reference goldens and the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import adapters as A
+from oracle import cases
+from test_oracle_golden import VAR_ATOL, logit_atol, state_tol
+
+pytestmark = pytest.mark.gpu
+
+
+def cu(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+@pytest.mark.parametrize("name", list(cases.HEAD))
+def test_head_vs_reference_golden(name, cuda_device):
+    import uniadapter_b200 as ua
+    inp = cases.head_inputs(name)
+    gold = load_golden(name, inp)
+    xn, logits, ent, prob, pred = ua.zero_shot_head(cu(inp["x"], cuda_device), cu(inp["text"], cuda_device))
+    # fp32 relative 1e-4 (north star); logits are O(1..10) sums of 512..1280 products
+    np.testing.assert_allclose(xn.cpu().numpy(), gold["xnorm"], rtol=1e-5, atol=1e-8)
+    np.testing.assert_allclose(logits.cpu().numpy(), gold["logits"], rtol=1e-4, atol=5e-5)
+    np.testing.assert_allclose(prob.cpu().numpy(), gold["prob"], rtol=2e-4, atol=1e-7)
+    np.testing.assert_allclose(ent.cpu().numpy(), gold["entropy"], rtol=2e-4, atol=1e-6)
+    np.testing.assert_array_equal(pred.cpu().numpy(), gold["pred"])
+    o = A.head(inp["x"], inp["text"])
+    np.testing.assert_allclose(logits.cpu().numpy(), o["logits"], rtol=1e-4, atol=5e-5)
+
+
+def test_get_logits_wrapper_signature(cuda_device):
+    import types
+    import uniadapter_b200 as ua
+    inp = cases.head_inputs("head_b1_d512_k40")
+    gold = load_golden("head_b1_d512_k40", inp)
+    x, text = cu(inp["x"], cuda_device), cu(inp["text"], cuda_device)
+    args = types.SimpleNamespace(vlm3d='ulip')
+    feats, logits, loss, prob_map, pred = ua.get_logits_wrapper(args, lambda xyz: x, torch.zeros(1, 4, 6, device=cuda_device),
+                                                                 text.t())
+    assert isinstance(pred, int) and pred == int(gold["pred"][0])
+    np.testing.assert_allclose(logits.cpu().numpy(), gold["logits"], rtol=1e-4, atol=5e-5)
+    np.testing.assert_allclose(loss.cpu().numpy(), gold["entropy"], rtol=2e-4, atol=1e-6)
+
+
+def run_mode_dota_cuda(inp, dev, fused=True):
+    import uniadapter_b200 as ua
+    cfg = cases.CFG
+    text = cu(inp["text"], dev)
+    x, xa = cu(inp["x"], dev), cu(inp["x_aug"], dev)
+    model = ua.DOTA_mix(cfg, inp["D"], inp["K"], text.t().contiguous(), num_modes=inp["M"], device=dev)
+    dls, finals, preds = [], [], []
+    for t in range(inp["T"]):
+        feats, clip_logits, _, prob_map, _ = ua.zero_shot_head(x[t], text)
+        xp = feats.mean(0).unsqueeze(0).half()
+        if fused:
+            dl = model.predict_then_fit(xp, feats, prob_map)
+        else:
+            dl = model.predict(xp)
+            model.fit(feats, prob_map)
+        model.fit(xa[t], prob_map)
+        model.update()
+        final, arg, _ = ua.fuse_logits(clip_logits, dl, model.c, cfg['rho'], cfg['eta'], feats.shape[0], 'mode_dota')
+        dls.append(dl.cpu().numpy()), finals.append(final.cpu().numpy()), preds.append(arg.cpu().numpy())
+    return model, np.stack(dls), np.stack(finals), np.stack(preds)
+
+
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("name", list(cases.MODEDOTA))
+def test_mode_dota_stream_vs_reference_golden(name, fused, cuda_device):
+    inp = cases.modedota_inputs(name)
+    gold = load_golden(name, inp)
+    model, dls, finals, preds = run_mode_dota_cuda(inp, cuda_device, fused)
+    np.testing.assert_allclose(dls, gold["dota_logits"], rtol=1e-4, atol=logit_atol(inp["D"]))
+    np.testing.assert_allclose(finals, gold["final_logits"], rtol=1e-4, atol=0.1 * logit_atol(inp["D"]))   # w <= eta = 0.1
+    np.testing.assert_array_equal(preds, gold["final_logits"].argmax(-1))          # per-step predictions, bit-exact
+    tol = state_tol(inp)
+    np.testing.assert_allclose(model.c.cpu().numpy(), gold["c"], rtol=1e-4, atol=tol["c"])
+    np.testing.assert_allclose(model.pi.cpu().numpy(), gold["pi"], rtol=1e-4, atol=tol["pi"])
+    np.testing.assert_allclose(model.class_counts.cpu().numpy(), gold["class_counts"], rtol=1e-5, atol=1e-6)
+    assert model.t == int(gold["t"])
+    mu, var = model.mu.cpu().numpy(), model.var.cpu().numpy()
+    if "mu" in gold:
+        np.testing.assert_allclose(mu, gold["mu"], rtol=1e-4, atol=tol["mu"])
+        np.testing.assert_allclose(var, gold["var"], rtol=1e-4, atol=VAR_ATOL)
+    else:
+        np.testing.assert_allclose(mu[:, :, ::8], gold["mu_sample"], rtol=1e-4, atol=tol["mu"])
+        np.testing.assert_allclose(var[:, :, ::8], gold["var_sample"], rtol=1e-4, atol=VAR_ATOL)
+
+
+def test_mode_dota_multi_stream_equals_single_streams(cuda_device):
+    """S adapters in one launch (state [S,K,M,D]) == S separate adapters."""
+    import uniadapter_b200 as ua
+    from uniadapter_b200 import _lib
+    from oracle import synth
+    S, K, M, D, B = 3, 11, 4, 96, 2
+    dev = cuda_device
+    cfg = cases.CFG
+    texts = [synth.unit_rows(K, D, 70 + s) for s in range(S)]
+    models = [ua.DOTA_mix(cfg, D, K, cu(t, dev).t().contiguous(), num_modes=M, device=dev) for t in texts]
+    mu = torch.stack([m.mu for m in models]).contiguous()
+    var = torch.stack([m.var for m in models]).contiguous()
+    pi = torch.stack([m.pi for m in models]).contiguous()
+    c = torch.stack([m.c for m in models]).contiguous()
+    cc = torch.stack([m.class_counts for m in models]).contiguous()
+    for step in range(3):
+        xs = [cu(synth.features(1, B, D, texts[s], 90 + 10 * step + s)[0][0], dev) for s in range(S)]
+        gs = [torch.softmax(100.0 * x @ cu(texts[s], dev).t(), 1) for s, x in enumerate(xs)]
+        xp = [x.mean(0, keepdim=True) for x in xs]
+        singles = [m.predict_then_fit(xp[s], xs[s], gs[s]) for s, m in enumerate(models)]
+        X, G_, XP = torch.stack(xs).contiguous(), torch.stack(gs).contiguous(), torch.stack(xp).contiguous()
+        out = torch.empty((S, 1, K), device=dev)
+        rc = _lib.lib().ua_modedota_step_f32(_lib.ptr(XP), 1, _lib.ptr(X), _lib.ptr(G_), B, K, 0, _lib.ptr(mu),
+                                             _lib.ptr(var), _lib.ptr(pi), _lib.ptr(c), _lib.ptr(cc), S, K, M, D,
+                                             float(cfg['epsilon']), _lib.ptr(out), K, 0, _lib.stream_ptr())
+        _lib.check(rc, "ua_modedota_step_f32")
+        for s in range(S):
+            assert torch.equal(out[s], singles[s])
+    for s, m in enumerate(models):
+        assert torch.equal(mu[s], m.mu) and torch.equal(var[s], m.var) and torch.equal(c[s], m.c)
+        assert torch.equal(pi[s], m.pi) and torch.equal(cc[s], m.class_counts)
+
+
+def test_mode_dota_lvis_scale_vs_oracle(cuda_device):
+    """cfg 4 size (K=1156, M=8, D=1024): persistent multi-class-per-CTA path, against the oracle."""
+    import uniadapter_b200 as ua
+    from oracle import synth
+    K, M, D = 1156, 8, 1024
+    cfg = cases.CFG
+    text = synth.unit_rows(K, D, 81)
+    x, xa, _ = synth.features(2, 1, D, text, 82)
+    dev = cuda_device
+    model = ua.DOTA_mix(cfg, D, K, cu(text, dev).t().contiguous(), num_modes=M, device=dev)
+    ora = A.ModeDota(cfg, D, K, text.T, M)
+    for t in range(2):
+        h = A.head(x[t], text)
+        xp = x[t].mean(axis=0, keepdims=True, dtype=np.float32).astype(np.float16).astype(np.float32)
+        dl_o = ora.predict(xp)
+        ora.fit(x[t], h["prob"]), ora.fit(xa[t], h["prob"])
+        dl = model.predict_then_fit(cu(xp, dev), cu(x[t], dev), cu(h["prob"], dev))
+        model.fit(cu(xa[t], dev), cu(h["prob"], dev))
+        np.testing.assert_allclose(dl.cpu().numpy(), dl_o, rtol=1e-4, atol=logit_atol(D))
+    tol = state_tol(dict(B=1, D=D))
+    np.testing.assert_allclose(model.mu.cpu().numpy(), ora.mu, rtol=1e-4, atol=tol["mu"])
+    np.testing.assert_allclose(model.var.cpu().numpy(), ora.var, rtol=1e-4, atol=VAR_ATOL)
+    np.testing.assert_allclose(model.c.cpu().numpy(), ora.c, rtol=1e-4, atol=tol["c"])
+    np.testing.assert_allclose(model.pi.cpu().numpy(), ora.pi, rtol=1e-4, atol=tol["pi"])
+    # size-independent property: every fit adds exactly sum_b sum_k gamma_class = B to the soft counts
+    assert abs(float(model.c.sum()) - (K + 2 * 2 * 1)) < 1e-2
+
+
+@pytest.mark.parametrize("name", list(cases.DOTA))
+def test_dota_stream_vs_reference_golden(name, cuda_device):
+    """Per-step DOTA loop against the reference goldens.
+
+    fit / state: fp32 tolerance. predict: evaluated with the REFERENCE's Lambda of that step injected, so that the
+    kernel's fp16 arithmetic is compared on identical inputs (a few half-ulps). update(): the library
+    inverse (cuSOLVER here, LAPACK in the golden) of a matrix with condition number ~1e3..1e4, then rounded to half,
+    is compared relative to the largest entry of Lambda.
+    """
+    import uniadapter_b200 as ua
+    inp = cases.dota_inputs(name)
+    gold = load_golden(name, inp)
+    cfg = cases.CFG
+    dev = cuda_device
+    D, K = inp["D"], inp["K"]
+    text, x = cu(inp["text"], dev), cu(inp["x"], dev)
+    model = ua.DOTA(cfg, D, K, torch.full((D, K), 0.001), device=dev)
+    for t in range(inp["T"]):
+        feats, clip_logits, _, prob_map, _ = ua.zero_shot_head(x[t], text)
+        xp = feats.mean(0).unsqueeze(0).half()
+        if t > 0:
+            model.Lambda = cu(gold["Lambda"][t - 1], dev)      # what the reference's predict used at this step
+        dl = model.predict(xp)
+        assert dl.dtype == torch.float16
+        model.fit(feats, prob_map)
+        model.update()
+        final, arg, _ = ua.fuse_logits(clip_logits, dl, model.c, cfg['rho'], cfg['eta'], feats.shape[0], 'dota')
+        ref = gold["dota_logits"][t].astype(np.float32)
+        np.testing.assert_allclose(dl.float().cpu().numpy(), ref, rtol=4e-3, atol=4e-3 * max(1.0, np.abs(ref).max()))
+        np.testing.assert_allclose(model.overall_Sigma.cpu().numpy(), gold["overall"][t], rtol=1e-4, atol=1e-9)
+        fr = gold["final_logits"][t]
+        np.testing.assert_allclose(final.cpu().numpy(), fr, rtol=4e-3, atol=4e-3 * np.abs(fr).max())
+        lam_ref = gold["Lambda"][t].astype(np.float32)
+        np.testing.assert_allclose(model.Lambda.float().cpu().numpy(), lam_ref, rtol=2e-2, atol=2e-2 * np.abs(lam_ref).max())
+    np.testing.assert_allclose(model.mu.cpu().numpy(), gold["mu"], rtol=1e-5, atol=1e-8)
+    np.testing.assert_allclose(model.c.cpu().numpy(), gold["c"], rtol=1e-6)
+    Sig = model.Sigma.cpu().numpy()
+    np.testing.assert_allclose(np.diagonal(Sig, axis1=1, axis2=2), gold["Sigma_diag"], rtol=1e-4, atol=1e-10)
+    np.testing.assert_allclose(Sig[0], gold["Sigma_k0"], rtol=1e-4, atol=1e-10)
+
+
+def test_dota_cfg1_size_fit_predict_vs_oracle(cuda_device):
+    """cfg 1 size (K=40, D=512): fit + predict against the oracle with a shared Lambda."""
+    import uniadapter_b200 as ua
+    from oracle import synth
+    K, D = 40, 512
+    cfg = cases.CFG
+    dev = cuda_device
+    text = synth.unit_rows(K, D, 91)
+    x, _, _ = synth.features(3, 1, D, text, 92)
+    model = ua.DOTA(cfg, D, K, torch.full((D, K), 0.001), device=dev)
+    ora = A.Dota(cfg, D, K, np.full((D, K), 0.001, dtype=np.float32))
+    for t in range(3):
+        h = A.head(x[t], text)
+        model.fit(cu(x[t], dev), cu(h["prob"], dev))
+        ora.fit(x[t], h["prob"])
+        np.testing.assert_allclose(model.overall_Sigma.cpu().numpy(), ora.overall, rtol=1e-4, atol=1e-9)
+        model.update()
+        # share the GPU's Lambda with the oracle so that predict is compared on identical inputs
+        ora.Lambda = model.Lambda.cpu().numpy()
+        xp = x[t].mean(axis=0, keepdims=True, dtype=np.float32)
+        dl = model.predict(cu(xp, dev).half()).float().cpu().numpy()
+        ref = ora.predict(xp).astype(np.float32)
+        np.testing.assert_allclose(dl, ref, rtol=2e-3, atol=2e-3 * max(1.0, np.abs(ref).max()))
+    np.testing.assert_allclose(model.Sigma.cpu().numpy(), ora.Sigma, rtol=1e-4, atol=1e-10)
+    np.testing.assert_allclose(model.mu.cpu().numpy(), ora.mu, rtol=1e-5, atol=1e-8)
+
+
+def test_fuse_kernel_vs_oracle(cuda_device):
+    import uniadapter_b200 as ua
+    rng = np.random.default_rng(3)
+    for K in (15, 40, 1156):
+        clip = (rng.standard_normal((1, K)) * 4).astype(np.float32)
+        dota = (rng.standard_normal((1, K)) * 300 - 900).astype(np.float32)
+        c = (rng.random((K, 8)) * 3).astype(np.float32)
+        final, arg, scaled = ua.fuse_logits(cu(clip, cuda_device), cu(dota, cuda_device), cu(c, cuda_device), 0.02, 0.1,
+                                            1, 'mode_dota', want_scaled=True)
+        f_o, d_o = A.fuse_mode_dota(clip, dota, c, 0.02, 0.1, 1)
+        np.testing.assert_allclose(scaled.cpu().numpy(), d_o, rtol=1e-6)
+        np.testing.assert_allclose(final.cpu().numpy(), f_o, rtol=1e-4, atol=1e-4)
+        assert int(arg[0]) == int(f_o.argmax())
+        # class-sharded form: the closed-form count replaces the device reduction
+        final2, _, _ = ua.fuse_logits(cu(clip, cuda_device), cu(dota, cuda_device), None, 0.02, 0.1, 1, 'mode_dota',
+                                      c_sum=float(c.sum(dtype=np.float64)), c_count=c.size)
+        np.testing.assert_allclose(final2.cpu().numpy(), final.cpu().numpy(), rtol=1e-5, atol=1e-5)

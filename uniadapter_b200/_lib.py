@@ -34,9 +34,9 @@ SIGNATURES = {
     "ua_knn_group_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _I, _P, _P, _P]),
     "ua_ball_group_f32": (_I, [_P, _P, _I, _P, _I, _I, _I, _F, _I, _P, _I, _P, _P]),
     "ua_gather_points_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
-    "ua_head_f32": (_I, [_P, _I, _I, _P, _I, _F, _P, _P, _P, _P, _P, _P]),
+    "ua_head_f32": (_I, [_P, _I, _I, _P, _I, _I, _F, _P, _P, _P, _P, _P, _P]),
     "ua_modedota_step_f32": (_I, [_P, _I, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _I, _I, _P]),
-    "ua_fuse_logits_f32": (_I, [_P, _P, _I, _I, _I, _P, _I, _F, _F, _F, _F, _F, _I, _P, _P, _P, _P]),
+    "ua_fuse_logits_f32": (_I, [_P, _P, _I, _I, _I, _P, _I, _I, _F, _F, _F, _F, _F, _I, _P, _P, _P, _P]),
     "ua_dota_fit_f32": (_I, [_P, _P, _I, _P, _P, _P, _P, _I, _I, _P]),
     "ua_dota_predict_f16": (_I, [_P, _I, _P, _P, _I, _I, _P, _P]),
     "ua_dota_regularize_f32": (_I, [_P, _I, _F, _P, _P]),

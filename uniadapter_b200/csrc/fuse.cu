@@ -50,7 +50,8 @@ __device__ __forceinline__ float softmax_entropy(F get, int K, float* s_tmp) {
 
 __global__ void __launch_bounds__(256)
     fuse_kernel(const float* __restrict__ clip, const void* __restrict__ dota, int dota_is_f16, int K,
-                const float* __restrict__ c, int count_c, float c_sum_override, float c_count_total, float rho,
+                const float* __restrict__ c, int count_c, int c_row_stride, float c_sum_override, float c_count_total,
+                float rho,
                 float eta, float batch, int mode, float* __restrict__ out_final, int* __restrict__ out_argmax,
                 float* __restrict__ out_scaled) {
   __shared__ float s_tmp[8];
@@ -64,7 +65,8 @@ __global__ void __launch_bounds__(256)
   float csum = c_sum_override;
   if (!(c_sum_override >= 0.f)) {
     float part = 0.f;
-    for (int i = threadIdx.x; i < count_c; i += blockDim.x) part += __ldg(c + i);
+    const float* crow_c = c + (size_t)r * c_row_stride;
+    for (int i = threadIdx.x; i < count_c; i += blockDim.x) part += __ldg(crow_c + i);
     csum = block_sum(part, s_tmp);
   }
   const float cmean = __fdiv_rn(csum, c_count_total);
@@ -115,16 +117,16 @@ __global__ void __launch_bounds__(256)
 }  // namespace ua
 
 extern "C" int ua_fuse_logits_f32(const float* clip_logits, const void* dota_logits, int dota_is_f16, int R, int K,
-                                  const float* c, int count_c, float c_sum_override, float c_count_total, float rho,
-                                  float eta, float batch, int mode, float* out_final, int32_t* out_argmax,
-                                  float* out_scaled_dota, void* stream) {
+                                  const float* c, int count_c, int c_row_stride, float c_sum_override,
+                                  float c_count_total, float rho, float eta, float batch, int mode, float* out_final,
+                                  int32_t* out_argmax, float* out_scaled_dota, void* stream) {
   using namespace ua;
   UA_REQUIRE(clip_logits && dota_logits && out_final, "ua_fuse_logits_f32: NULL pointer");
   UA_REQUIRE(R >= 1 && K >= 1, "ua_fuse_logits_f32: bad sizes R=%d K=%d", R, K);
   UA_REQUIRE(c_sum_override >= 0.f || (c && count_c >= 1), "ua_fuse_logits_f32: need c[] or c_sum_override");
   UA_REQUIRE(c_count_total > 0.f && batch > 0.f, "ua_fuse_logits_f32: c_count_total and batch must be > 0");
   UA_REQUIRE(mode == 0 || mode == 1, "ua_fuse_logits_f32: mode must be 0 or 1");
-  fuse_kernel<<<R, 256, 0, (cudaStream_t)stream>>>(clip_logits, dota_logits, dota_is_f16, K, c, count_c,
+  fuse_kernel<<<R, 256, 0, (cudaStream_t)stream>>>(clip_logits, dota_logits, dota_is_f16, K, c, count_c, c_row_stride,
                                                    c_sum_override, c_count_total, rho, eta, batch, mode, out_final,
                                                    out_argmax, out_scaled_dota);
   return check_launch("ua_fuse_logits_f32");

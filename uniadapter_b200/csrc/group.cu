@@ -6,11 +6,13 @@
 //   ball_group_kernel: first-nsample-in-index-order ball query, fused with the same epilogue
 //                      (models/openshape/pointnet_util.py:89-146).
 //
-// One warp owns one centre. A CTA's warps share point tiles staged in shared memory (coordinates AoS, stride-3
-// reads are bank-conflict free, plus the per-point squared norm). The (G,N) distance matrix of the reference is
-// never written. kNN selection is a streaming filter: candidates below the running threshold are ballot-compacted
-// into a per-warp shared-memory buffer of 64-bit (distance,index) keys; when the buffer fills, a warp-wide bitonic
-// sort keeps the k best and tightens the threshold (O(log(N/k)) sorts per centre).
+// One warp owns one centre. A CTA's warps share point tiles that the TMA unit double-buffers in shared memory
+// (coordinates AoS: stride-3 reads are bank-conflict free; plus the per-point squared norm). The (G,N) distance
+// matrix of the reference is never written. kNN selection is a streaming filter: candidates below the running
+// threshold are ballot-compacted into a per-warp shared-memory buffer; when it fills, a register-resident radix
+// select (bitwise binary search, one REDUX per bit) keeps the k best and tightens the threshold -- O(log(N/k))
+// selections per centre, no sort anywhere: the buffer stays in ascending point-index order, which is also the
+// order the neighbours are emitted in.
 #include "common.cuh"
 
 namespace ua {
@@ -19,60 +21,142 @@ int g_knn_warps = 0;  // tuning override (0 = heuristic)
 
 namespace {
 
-constexpr int kTilePoints = 2048;
+constexpr int kTilePoints = 1024;
 constexpr uint64_t kKeyMax = ~0ull;
 
-__device__ __forceinline__ void stage_tile(const float* __restrict__ cloud, int t0, int tp, float* s_xyz,
-                                           float* s_pn) {
-  __syncthreads();  // previous tile fully consumed
-  const float* src = cloud + (size_t)3 * t0;
-  for (int i = threadIdx.x; i < 3 * tp; i += blockDim.x) s_xyz[i] = __ldg(src + i);
-  __syncthreads();
-  for (int p = threadIdx.x; p < tp; p += blockDim.x)
-    s_pn[p] = sqnorm_nofma(s_xyz[3 * p], s_xyz[3 * p + 1], s_xyz[3 * p + 2]);
-  __syncthreads();
-}
+// ---- point-tile pipeline shared by both grouping kernels ---------------------------------------------------
+// Tiles of up to kTilePoints points (AoS xyz, 12 KB) are double-buffered in shared memory. When the cloud is
+// 16-byte tileable (N % 4 == 0, aligned base) the TMA unit fills the next tile with one bulk copy while the
+// warps scan the current one; otherwise the CTA copies cooperatively.
+struct TileSmem {
+  float xyz[2][3 * kTilePoints];
+  float pn[2][kTilePoints];
+  uint64_t bar[2];
+};
 
-// Ascending bitonic sort of CAP 64-bit keys in shared memory by one warp.
-template <int CAP>
-__device__ __forceinline__ void warp_bitonic_sort(uint64_t* buf, int lane) {
-#pragma unroll 1
-  for (int size = 2; size <= CAP; size <<= 1) {
-#pragma unroll 1
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-#pragma unroll
-      for (int t = lane; t < CAP / 2; t += 32) {
-        const int i = 2 * t - (t & (stride - 1));
-        const int j = i + stride;
-        const bool asc = (i & size) == 0;
-        const uint64_t a = buf[i], b = buf[j];
-        if ((a > b) == asc) {
-          buf[i] = b;
-          buf[j] = a;
-        }
-      }
-      __syncwarp();
+struct TilePipe {
+  TileSmem* sm;
+  const float* cloud;
+  int N, ntiles, bulk;
+  uint32_t phase;
+
+  __device__ __forceinline__ void init(TileSmem* s, const float* c, int n, int use_bulk) {
+    sm = s, cloud = c, N = n, bulk = use_bulk, phase = 0;
+    ntiles = (n + kTilePoints - 1) / kTilePoints;
+    if (bulk && threadIdx.x == 0) {
+      mbar_init(&sm->bar[0], 1);
+      mbar_init(&sm->bar[1], 1);
+      fence_mbar_init();
     }
+    __syncthreads();
+    if (bulk && threadIdx.x == 0) issue(0);
   }
+  __device__ __forceinline__ int tile_points(int t) const { return min(kTilePoints, N - t * kTilePoints); }
+  __device__ __forceinline__ void issue(int t) {
+    const int st = t & 1;
+    const uint32_t bytes = (uint32_t)tile_points(t) * 12u;
+    mbar_expect_tx(&sm->bar[st], bytes);
+    bulk_g2s(sm->xyz[st], cloud + (size_t)3 * t * kTilePoints, bytes, &sm->bar[st]);
+  }
+  // Makes tile t resident (coordinates + squared norms) for every thread of the CTA; returns its stage.
+  __device__ __forceinline__ int acquire(int t) {
+    const int st = t & 1;
+    const int tp = tile_points(t);
+    if (bulk) {
+      if (threadIdx.x == 0 && t + 1 < ntiles) issue(t + 1);  // stage st^1 was released by the barrier in release()
+      mbar_wait(&sm->bar[st], (phase >> st) & 1u);
+      phase ^= 1u << st;
+    } else {
+      const float* src = cloud + (size_t)3 * t * kTilePoints;
+      for (int i = threadIdx.x; i < 3 * tp; i += blockDim.x) sm->xyz[st][i] = __ldg(src + i);
+      __syncthreads();
+    }
+    for (int p = threadIdx.x; p < tp; p += blockDim.x)
+      sm->pn[st][p] = sqnorm_nofma(sm->xyz[st][3 * p], sm->xyz[st][3 * p + 1], sm->xyz[st][3 * p + 2]);
+    __syncthreads();
+    return st;
+  }
+  __device__ __forceinline__ void release() { __syncthreads(); }
+};
+
+// ---- kNN selection -------------------------------------------------------------------------------------------
+// Per warp: a shared-memory buffer of CAP (distance-key, index) pairs, always in ascending point-index order
+// (appends follow the scan order and compaction is a stable filter). When the buffer cannot take another
+// batch, the warp finds the k-th smallest distance key by a bitwise binary search over register-held keys
+// (one REDUX add per bit), keeps the keys below it plus the lowest-index ties, and tightens the threshold.
+template <int CAP>
+__device__ __forceinline__ void knn_compact(uint32_t* bkey, uint32_t* bidx, int& count, int k, int lane,
+                                            uint64_t& thr) {
+  constexpr int R = CAP / 32;
+  __syncwarp();
+  uint32_t key[R], idx[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int e = r * 32 + lane;
+    key[r] = e < count ? bkey[e] : 0xffffffffu;
+    idx[r] = e < count ? bidx[e] : 0xffffffffu;
+  }
+  // k-th smallest key: the largest T with count(key < T) < k
+  uint32_t T = 0;
+#pragma unroll 1
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t cand = T | (1u << bit);
+    int c = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) c += key[r] < cand;
+    c = __reduce_add_sync(kFullMask, c);
+    if (c < k) T = cand;
+  }
+  int nless = 0;
+#pragma unroll
+  for (int r = 0; r < R; ++r) nless += key[r] < T;
+  nless = __reduce_add_sync(kFullMask, nless);
+  const int need_eq = k - nless;  // >= 1 by construction of T
+  const unsigned lt_mask = (1u << lane) - 1u;
+  __syncwarp();
+  int eq_seen = 0, out = 0;
+  uint32_t last_eq_idx = 0;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const bool eq = key[r] == T;
+    const unsigned meq = __ballot_sync(kFullMask, eq);
+    const int eq_rank = eq_seen + __popc(meq & lt_mask);
+    const bool keep = key[r] < T || (eq && eq_rank < need_eq);
+    // the tie that fills the k-th slot carries the threshold index
+    const unsigned mlast = __ballot_sync(kFullMask, eq && eq_rank == need_eq - 1);
+    if (mlast) last_eq_idx = __shfl_sync(kFullMask, idx[r], __ffs(mlast) - 1);
+    eq_seen += __popc(meq);
+    const unsigned mk = __ballot_sync(kFullMask, keep);
+    if (keep) {
+      const int pos = out + __popc(mk & lt_mask);
+      bkey[pos] = key[r];
+      bidx[pos] = idx[r];
+    }
+    out += __popc(mk);
+  }
+  __syncwarp();
+  count = out;  // == k
+  thr = ((uint64_t)T << 32) | last_eq_idx;
 }
 
 template <int CAP, typename IdxT>
 __global__ void __launch_bounds__(256)
     knn_group_kernel(const float* __restrict__ xyz, const float* __restrict__ rgb, const float* __restrict__ centers,
-                     int N, int G, int k, IdxT* __restrict__ out_idx, float* __restrict__ out_neigh,
+                     int N, int G, int k, int use_bulk, IdxT* __restrict__ out_idx, float* __restrict__ out_neigh,
                      float* __restrict__ out_feat) {
-  extern __shared__ __align__(16) unsigned char s_raw[];
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  TileSmem* tiles = reinterpret_cast<TileSmem*>(s_raw);
+  uint32_t* s_key = reinterpret_cast<uint32_t*>(s_raw + sizeof(TileSmem));  // [W][CAP]
   const int W = blockDim.x >> 5;
-  uint64_t* s_buf = reinterpret_cast<uint64_t*>(s_raw);                    // [W][CAP]
-  float* s_xyz = reinterpret_cast<float*>(s_raw + (size_t)W * CAP * 8);    // [3*kTilePoints]
-  float* s_pn = s_xyz + 3 * kTilePoints;                                   // [kTilePoints]
+  uint32_t* s_idx = s_key + (size_t)W * CAP;                                // [W][CAP]
 
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = blockIdx.x * W + warp;
   const bool active = g < G;
   const float* cloud = xyz + (size_t)b * N * 3;
-  uint64_t* buf = s_buf + (size_t)warp * CAP;
+  uint32_t* bkey = s_key + (size_t)warp * CAP;
+  uint32_t* bidx = s_idx + (size_t)warp * CAP;
 
   float cx = 0.f, cy = 0.f, cz = 0.f, cn = 0.f;
   if (active) {
@@ -84,43 +168,44 @@ __global__ void __launch_bounds__(256)
   uint64_t thr = kKeyMax;
   const unsigned lt_mask = (1u << lane) - 1u;
 
-  for (int t0 = 0; t0 < N; t0 += kTilePoints) {
-    const int tp = min(kTilePoints, N - t0);
-    stage_tile(cloud, t0, tp, s_xyz, s_pn);
-    if (!active) continue;
-    for (int base = 0; base < tp; base += 32) {
-      const int p = base + lane;
-      uint64_t key = kKeyMax;
-      if (p < tp) {
-        const float d = expanded_sqdist(cx, cy, cz, cn, s_xyz[3 * p], s_xyz[3 * p + 1], s_xyz[3 * p + 2], s_pn[p]);
-        key = ((uint64_t)float_to_ordered(d) << 32) | (uint32_t)(t0 + p);
-      }
-      const bool take = key < thr;  // kKeyMax is never < thr
-      const unsigned m = __ballot_sync(kFullMask, take);
-      if (m) {
-        if (take) buf[count + __popc(m & lt_mask)] = key;
-        count += __popc(m);
-        if (count > CAP - 32) {  // not enough room for another full batch: keep the k best, tighten the threshold
-          __syncwarp();
-          for (int i = count + lane; i < CAP; i += 32) buf[i] = kKeyMax;
-          __syncwarp();
-          warp_bitonic_sort<CAP>(buf, lane);
-          count = min(count, k);
-          thr = count == k ? buf[k - 1] : kKeyMax;
+  TilePipe pipe;
+  pipe.init(tiles, cloud, N, use_bulk);
+  for (int t = 0; t < pipe.ntiles; ++t) {
+    const int st = pipe.acquire(t);
+    if (active) {
+      const float* sx = tiles->xyz[st];
+      const float* sp = tiles->pn[st];
+      const int tp = pipe.tile_points(t), t0 = t * kTilePoints;
+      for (int base = 0; base < tp; base += 32) {
+        const int p = base + lane;
+        uint64_t key = kKeyMax;
+        if (p < tp) {
+          const float d = expanded_sqdist(cx, cy, cz, cn, sx[3 * p], sx[3 * p + 1], sx[3 * p + 2], sp[p]);
+          key = ((uint64_t)float_to_ordered(d) << 32) | (uint32_t)(t0 + p);
+        }
+        const bool take = key < thr;  // kKeyMax is never < thr
+        const unsigned m = __ballot_sync(kFullMask, take);
+        if (m) {
+          if (take) {
+            const int pos = count + __popc(m & lt_mask);
+            bkey[pos] = (uint32_t)(key >> 32);
+            bidx[pos] = (uint32_t)key;
+          }
+          count += __popc(m);
+          if (count > CAP - 32) knn_compact<CAP>(bkey, bidx, count, k, lane, thr);
         }
       }
     }
+    pipe.release();
   }
   if (!active) return;
+  if (count > k) knn_compact<CAP>(bkey, bidx, count, k, lane, thr);
   __syncwarp();
-  for (int i = count + lane; i < CAP; i += 32) buf[i] = kKeyMax;
-  __syncwarp();
-  warp_bitonic_sort<CAP>(buf, lane);
 
-  // epilogue: nearest-first indices, gather, centre subtraction, concat
+  // epilogue: ascending point index, gather, centre subtraction, concat
   const size_t row0 = ((size_t)b * G + g) * k;
   for (int j = lane; j < k; j += 32) {
-    const uint32_t p = (uint32_t)(buf[j] & 0xffffffffull);
+    const uint32_t p = bidx[j];
     if (out_idx) out_idx[row0 + j] = (IdxT)p;
     const float* src = cloud + (size_t)3 * p;
     const float nx = __fsub_rn(__ldg(src), cx), ny = __fsub_rn(__ldg(src + 1), cy), nz = __fsub_rn(__ldg(src + 2), cz);
@@ -141,13 +226,12 @@ __global__ void __launch_bounds__(256)
 template <typename IdxT>
 __global__ void __launch_bounds__(256)
     ball_group_kernel(const float* __restrict__ xyz, const float* __restrict__ feat, int C,
-                      const float* __restrict__ centers, int N, int S, float radius2, int nsample,
+                      const float* __restrict__ centers, int N, int S, float radius2, int nsample, int use_bulk,
                       IdxT* __restrict__ out_idx, float* __restrict__ out_new_points) {
-  extern __shared__ __align__(16) unsigned char s_raw[];
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  TileSmem* tiles = reinterpret_cast<TileSmem*>(s_raw);
+  int* s_sel = reinterpret_cast<int*>(s_raw + sizeof(TileSmem));  // [W][nsample]
   const int W = blockDim.x >> 5;
-  int* s_sel = reinterpret_cast<int*>(s_raw);                                   // [W][nsample]
-  float* s_xyz = reinterpret_cast<float*>(s_raw + (((size_t)W * nsample * 4 + 15) / 16) * 16);
-  float* s_pn = s_xyz + 3 * kTilePoints;
 
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -165,25 +249,31 @@ __global__ void __launch_bounds__(256)
   int count = 0;
   const unsigned lt_mask = (1u << lane) - 1u;
 
-  for (int t0 = 0; t0 < N; t0 += kTilePoints) {
-    // every warp of the CTA must take part in staging even when its own ball is already full
-    const int tp = min(kTilePoints, N - t0);
-    stage_tile(cloud, t0, tp, s_xyz, s_pn);
-    if (!active || count >= nsample) continue;
-    for (int base = 0; base < tp && count < nsample; base += 32) {
-      const int p = base + lane;
-      bool inside = false;
-      if (p < tp) {
-        const float d = expanded_sqdist(cx, cy, cz, cn, s_xyz[3 * p], s_xyz[3 * p + 1], s_xyz[3 * p + 2], s_pn[p]);
-        inside = !(d > radius2);  // the reference marks d > r^2 as outside
-      }
-      const unsigned m = __ballot_sync(kFullMask, inside);
-      if (m) {
-        const int pos = count + __popc(m & lt_mask);
-        if (inside && pos < nsample) sel[pos] = t0 + p;
-        count += __popc(m);
+  TilePipe pipe;
+  pipe.init(tiles, cloud, N, use_bulk);
+  for (int t = 0; t < pipe.ntiles; ++t) {
+    // every warp of the CTA takes part in the tile hand-over even when its own ball is already full
+    const int st = pipe.acquire(t);
+    if (active && count < nsample) {
+      const float* sx = tiles->xyz[st];
+      const float* sp = tiles->pn[st];
+      const int tp = pipe.tile_points(t), t0 = t * kTilePoints;
+      for (int base = 0; base < tp && count < nsample; base += 32) {
+        const int p = base + lane;
+        bool inside = false;
+        if (p < tp) {
+          const float d = expanded_sqdist(cx, cy, cz, cn, sx[3 * p], sx[3 * p + 1], sx[3 * p + 2], sp[p]);
+          inside = !(d > radius2);  // the reference marks d > r^2 as outside
+        }
+        const unsigned m = __ballot_sync(kFullMask, inside);
+        if (m) {
+          const int pos = count + __popc(m & lt_mask);
+          if (inside && pos < nsample) sel[pos] = t0 + p;
+          count += __popc(m);
+        }
       }
     }
+    pipe.release();
   }
   if (!active) return;
   __syncwarp();
@@ -219,16 +309,16 @@ int pick_warps(int B, int G) {
   if (g_knn_warps > 0) return g_knn_warps;
   // enough CTAs to cover the 148 SMs a few times over, as many centres per staged tile as that allows
   const long long centres = (long long)B * G;
-  if (centres >= 8LL * 4 * kNumSMs) return 8;
-  if (centres >= 4LL * 2 * kNumSMs) return 4;
-  return 2;
+  if (centres >= 8LL * 2 * kNumSMs) return 8;
+  return 4;
 }
 
 template <int CAP, typename IdxT>
 int launch_knn(const float* xyz, const float* rgb, const float* centers, int B, int N, int G, int k, void* out_idx,
                float* out_neigh, float* out_feat, cudaStream_t st) {
   const int W = pick_warps(B, G);
-  const size_t smem = (size_t)W * CAP * 8 + (size_t)4 * kTilePoints * sizeof(float);
+  const size_t smem = sizeof(TileSmem) + (size_t)W * CAP * 8;
+  const int use_bulk = (N % 4 == 0) && ((uintptr_t)xyz % 16 == 0);
   auto kern = knn_group_kernel<CAP, IdxT>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -238,13 +328,14 @@ int launch_knn(const float* xyz, const float* rgb, const float* centers, int B, 
     }
   }
   dim3 grid((G + W - 1) / W, B);
-  kern<<<grid, W * 32, smem, st>>>(xyz, rgb, centers, N, G, k, (IdxT*)out_idx, out_neigh, out_feat);
+  kern<<<grid, W * 32, smem, st>>>(xyz, rgb, centers, N, G, k, use_bulk, (IdxT*)out_idx, out_neigh, out_feat);
   return check_launch("ua_knn_group_f32");
 }
 
 template <typename IdxT>
 int dispatch_knn(const float* xyz, const float* rgb, const float* centers, int B, int N, int G, int k, void* out_idx,
                  float* out_neigh, float* out_feat, cudaStream_t st) {
+  // buffer capacity: room for at least k fresh candidates (plus one 32-wide batch) between compactions
   if (k <= 48) return launch_knn<128, IdxT>(xyz, rgb, centers, B, N, G, k, out_idx, out_neigh, out_feat, st);
   if (k <= 112) return launch_knn<256, IdxT>(xyz, rgb, centers, B, N, G, k, out_idx, out_neigh, out_feat, st);
   return launch_knn<512, IdxT>(xyz, rgb, centers, B, N, G, k, out_idx, out_neigh, out_feat, st);
@@ -281,17 +372,19 @@ extern "C" int ua_ball_group_f32(const float* xyz, const float* feat, int C, con
   if (B == 0) return UA_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int W = pick_warps(B, S);
-  const size_t smem = (((size_t)W * nsample * 4 + 15) / 16) * 16 + (size_t)4 * kTilePoints * sizeof(float);
+  const size_t smem = sizeof(TileSmem) + (size_t)W * nsample * 4;
+  const int use_bulk = (N % 4 == 0) && ((uintptr_t)xyz % 16 == 0);
   dim3 grid((S + W - 1) / W, B);
   if (idx_is_i64) {
     auto kern = ball_group_kernel<long long>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<grid, W * 32, smem, st>>>(xyz, feat, C, centers, N, S, radius2, nsample, (long long*)out_idx,
+    kern<<<grid, W * 32, smem, st>>>(xyz, feat, C, centers, N, S, radius2, nsample, use_bulk, (long long*)out_idx,
                                      out_new_points);
   } else {
     auto kern = ball_group_kernel<int>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<grid, W * 32, smem, st>>>(xyz, feat, C, centers, N, S, radius2, nsample, (int*)out_idx, out_new_points);
+    kern<<<grid, W * 32, smem, st>>>(xyz, feat, C, centers, N, S, radius2, nsample, use_bulk, (int*)out_idx,
+                                     out_new_points);
   }
   return check_launch("ua_ball_group_f32");
 }

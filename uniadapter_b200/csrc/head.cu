@@ -28,13 +28,19 @@ __global__ void __launch_bounds__(256) l2norm_kernel(const float* __restrict__ x
   for (int d = threadIdx.x; d < D; d += blockDim.x) out[(size_t)b * D + d] = __fdiv_rn(__ldg(row + d), nrm);
 }
 
-// logits[b,k] = sum_d (scale * xnorm[b,d]) * text[k,d]; one warp per class k.
+// logits[b,k] = sum_d (scale * xnorm[b,d]) * text[g(b)][k,d]; one warp per class k, blockIdx.y = text group
+// (rows [g*rows_per_group, (g+1)*rows_per_group) use text matrix g; a single shared matrix is group 0 of 1).
 __global__ void __launch_bounds__(256)
-    logits_kernel(const float* __restrict__ xnorm, int B, int D, const float* __restrict__ text, int K, float scale,
-                  float* __restrict__ logits) {
+    logits_kernel(const float* __restrict__ xnorm, int rows_per_group, int D, const float* __restrict__ text_all, int K,
+                  float scale, float* __restrict__ logits_all) {
   extern __shared__ __align__(16) float s_x[];  // [kRowsPerPass][D] scaled rows
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
   const int k = blockIdx.x * W + warp;
+  const int grp = blockIdx.y;
+  const int B = rows_per_group;
+  const float* text = text_all + (size_t)grp * K * D;
+  xnorm += (size_t)grp * B * D;
+  float* logits = logits_all + (size_t)grp * B * K;
   const float* trow = text + (size_t)(k < K ? k : 0) * D;
   const bool vec = (D & 3) == 0;
   for (int b0 = 0; b0 < B; b0 += kRowsPerPass) {
@@ -155,12 +161,14 @@ int launch_l2norm(const float* x, int B, int D, float* out, cudaStream_t st) {
 
 }  // namespace ua
 
-extern "C" int ua_head_f32(const float* x, int B, int D, const float* text, int K, float scale, float* out_xnorm,
-                           float* out_logits, float* out_prob, float* out_entropy, int32_t* out_argmax,
-                           void* stream) {
+extern "C" int ua_head_f32(const float* x, int B, int D, const float* text, int num_text, int K, float scale,
+                           float* out_xnorm, float* out_logits, float* out_prob, float* out_entropy,
+                           int32_t* out_argmax, void* stream) {
   using namespace ua;
   UA_REQUIRE(x && text && out_logits && out_xnorm, "ua_head_f32: x/text/out_logits/out_xnorm must be non-NULL");
   UA_REQUIRE(B >= 0 && D >= 1 && K >= 1, "ua_head_f32: bad sizes B=%d D=%d K=%d", B, D, K);
+  UA_REQUIRE(num_text >= 1 && B % num_text == 0, "ua_head_f32: B=%d must be a multiple of num_text=%d", B, num_text);
+  UA_REQUIRE(num_text <= 65535, "ua_head_f32: num_text=%d > 65535", num_text);
   if (B == 0) return UA_OK;
   cudaStream_t st = (cudaStream_t)stream;
   int rc = launch_l2norm(x, B, D, out_xnorm, st);
@@ -169,7 +177,8 @@ extern "C" int ua_head_f32(const float* x, int B, int D, const float* text, int 
   const size_t smem = (size_t)kRowsPerPass * D * sizeof(float);
   UA_UNSUPPORTED(smem > 200 * 1024, "ua_head_f32: D=%d too large", D);
   if (smem > 48 * 1024) cudaFuncSetAttribute(logits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  logits_kernel<<<(K + W - 1) / W, W * 32, smem, st>>>(out_xnorm, B, D, text, K, scale, out_logits);
+  dim3 grid((K + W - 1) / W, num_text);
+  logits_kernel<<<grid, W * 32, smem, st>>>(out_xnorm, B / num_text, D, text, K, scale, out_logits);
   rc = check_launch("ua_head_f32(logits)");
   if (rc != UA_OK) return rc;
   if (out_prob || out_entropy || out_argmax) return launch_row_stats(out_logits, B, K, out_prob, out_entropy, out_argmax, st);

@@ -11,12 +11,14 @@ from . import _lib
 
 
 def zero_shot_head(x: torch.Tensor, text: torch.Tensor, scale: float = 100.0, *, want_prob: bool = True):
-    """x (B,D) raw encoder output, text (K,D) -> (xnorm, logits, entropy, prob, argmax int32 (B,))."""
+    """x (B,D) raw encoder output, text (K,D) [or (S,K,D): one matrix per block of B/S rows]
+    -> (xnorm, logits, entropy, prob, argmax int32 (B,))."""
     x = x.float().contiguous()
     text = text.float().contiguous()
     B, D = x.shape
-    K = text.shape[0]
-    if text.shape[1] != D:
+    num_text = 1 if text.dim() == 2 else text.shape[0]
+    K = text.shape[-2]
+    if text.shape[-1] != D:
         raise ValueError(f"text features {tuple(text.shape)} do not match feature dim {D}")
     dev = x.device
     xnorm = torch.empty_like(x)
@@ -24,7 +26,7 @@ def zero_shot_head(x: torch.Tensor, text: torch.Tensor, scale: float = 100.0, *,
     prob = torch.empty((B, K), dtype=torch.float32, device=dev) if want_prob else None
     entropy = torch.empty((B,), dtype=torch.float32, device=dev)
     argmax = torch.empty((B,), dtype=torch.int32, device=dev)
-    rc = _lib.lib().ua_head_f32(_lib.ptr(x), B, D, _lib.ptr(text), K, float(scale), _lib.ptr(xnorm), _lib.ptr(logits),
+    rc = _lib.lib().ua_head_f32(_lib.ptr(x), B, D, _lib.ptr(text), num_text, K, float(scale), _lib.ptr(xnorm), _lib.ptr(logits),
                                 _lib.ptr(prob), _lib.ptr(entropy), _lib.ptr(argmax), _lib.stream_ptr())
     _lib.check(rc, "ua_head_f32")
     return xnorm, logits, entropy, prob, argmax

@@ -60,7 +60,8 @@ def knn_group(xyz: torch.Tensor, centers: torch.Tensor, k: int, rgb: torch.Tenso
               idx_dtype: torch.dtype = torch.int64):
     """k nearest points of every centre + gather + centre subtraction (+ colour concat).
 
-    Returns (idx (B,G,k) | None, neigh (B,G,k,3) | None, feat (B,G,k,6) | None); neighbours nearest first.
+    Returns (idx (B,G,k) | None, neigh (B,G,k,3) | None, feat (B,G,k,6) | None); neighbours in ascending
+    point-index order (the reference's topk(sorted=False) order is unspecified).
     """
     xyz = _f32c(xyz)
     centers = _f32c(centers)
@@ -159,7 +160,7 @@ def farthest_point_sample(xyz: torch.Tensor, npoint: int, start_idx: torch.Tenso
 
 
 def knn_point(nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor) -> torch.Tensor:
-    """knn_point(nsample, xyz, new_xyz) -> (B,S,nsample) int64 (nearest first; the reference's order is unspecified)."""
+    """knn_point(nsample, xyz, new_xyz) -> (B,S,nsample) int64 (ascending index; the reference's order is unspecified)."""
     idx, _, _ = knn_group(xyz, new_xyz, nsample, want_idx=True, want_neigh=False, want_feat=False)
     return idx
 
