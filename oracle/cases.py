@@ -58,6 +58,22 @@ ALIGN = {
 }
 
 
+# name -> (T steps, N points, K classes, M modes, encoder depth, res_learning, seed)
+E2E = {
+    "e2e_ulip_d2_modedota_res": (8, 1024, 40, 8, 2, True, 71),
+    "e2e_ulip_d2_modedota": (8, 1024, 40, 8, 2, False, 72),
+    "e2e_ulip_d2_dota": (6, 1024, 40, 0, 2, False, 73),
+}
+E2E_MODEL_SEED = 0
+E2E_LOOP_SEED = 123
+
+
+def e2e_inputs(name):
+    T, N, K, M, depth, res, seed = E2E[name]
+    return dict(pc=synth.cloud(T, N, seed), text=synth.unit_rows(K, 512, seed + 1), T=T, N=N, K=K, M=M, depth=depth,
+                res_learning=res)
+
+
 def tok_knn_inputs(name):
     B, N, G, k, seed, mode = TOK_KNN[name]
     xyz = synth.cloud(B, N, seed)

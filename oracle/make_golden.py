@@ -180,6 +180,94 @@ def alignment_goldens():
              grad=res.grad)
 
 
+def e2e_goldens():
+    """The reference's per-sample loop (Uni_Adapter.py:368-579, batch 1) with its own ULIP PointBERT modules,
+    get_logits_wrapper, DOTA / DOTA_mix, compute_text_alignment_loss and Adam, run on the CPU. The loop body is
+    restated here only because test_zeroshot_3d_core hard-codes torch.cuda events; every numerical call is the
+    reference's. Also checks that uniadapter_b200.encoders.UlipPointBert reproduces the reference's random init."""
+    import torch.nn.functional as F
+    from uniadapter_b200.encoders import UlipPointBert
+    _, _, penc = R.ulip_pointbert()
+    ua = R.uni_adapter()
+    dm, dt = R.dota_mixture(), R.dota()
+    for name in cases.E2E:
+        inp = cases.e2e_inputs(name)
+        T, N, K, M, depth = inp["T"], inp["N"], inp["K"], inp["M"], inp["depth"]
+        margs = types.SimpleNamespace(pc_feat_dim=768, pc_depth=depth, drop_path_rate=0.0, num_head=6, group_size=32,
+                                      num_group=512, encoder_dim=256)
+        torch.manual_seed(cases.E2E_MODEL_SEED)
+        trunk = penc.PointTransformer(margs)                       # models/ulip/pointbert/point_encoder.py:103
+        proj = torch.empty(768, 512)
+        torch.nn.init.normal_(proj, std=768 ** -0.5)
+        trunk.eval()
+        model = lambda xyz: trunk(xyz) @ proj                      # models/ulip/ulip_model.py:15-18
+        torch.manual_seed(cases.E2E_MODEL_SEED)
+        mine = UlipPointBert(depth=depth).eval()
+        ref_sd = list(trunk.state_dict().values())
+        my_sd = [v for k, v in mine.state_dict().items() if k != "pc_projection"]
+        assert len(ref_sd) == len(my_sd) and all(torch.equal(a, b) for a, b in zip(ref_sd, my_sd)), "init mismatch"
+        assert torch.equal(mine.pc_projection, proj)
+
+        text = T_(inp["text"])
+        pcs = T_(inp["pc"])
+        args = types.SimpleNamespace(vlm3d='ulip')
+        use_mode = M > 0
+        if use_mode:
+            adapter = dm.DOTA_mix(CFG, 512, K, text.t().contiguous(), num_modes=M)
+        else:
+            adapter = dt.DOTA(CFG, 512, K, torch.full((512, K), 0.001))
+        if inp["res_learning"]:
+            res = torch.zeros_like(text, requires_grad=True)
+            opt = torch.optim.Adam([res], lr=0.001)
+        torch.manual_seed(cases.E2E_LOOP_SEED)
+        finals, clips, dls = [], [], []
+        with torch.no_grad():
+            for i in range(T):
+                pc = pcs[i:i + 1]
+                rgb = torch.ones_like(pc)
+                feature = torch.cat((pc, rgb), dim=-1)
+                if inp["res_learning"]:
+                    clip_weights = F.normalize(text + res.detach(), dim=1).t()
+                else:
+                    clip_weights = text.t()
+                feats, clip_logits, loss, prob_map, pred = ua.get_logits_wrapper(args, model, feature, clip_weights)
+                dl = adapter.predict(feats.mean(0).unsqueeze(0).half())
+                adapter.fit(feats, prob_map)
+                if use_mode:
+                    pc_aug = pc + 0.05 * torch.randn_like(pc)
+                    feats_aug, _, _, _, _ = ua.get_logits_wrapper(args, model, torch.cat((pc_aug, rgb), dim=-1), clip_weights)
+                    feats_aug = feats_aug / feats_aug.norm(dim=-1, keepdim=True)
+                    adapter.fit(feats_aug, prob_map)
+                    adapter.update()
+                    if i > 0 and inp["res_learning"]:
+                        with torch.enable_grad():
+                            emb = text + res
+                            emb = emb / emb.norm(dim=1, keepdim=True)
+                            al, _ = ua.compute_text_alignment_loss(emb, adapter)
+                            for _ in range(10):
+                                opt.zero_grad()
+                                al.backward()
+                                opt.step()
+                                emb = text + res
+                                emb = emb / emb.norm(dim=1, keepdim=True)
+                                al, _ = ua.compute_text_alignment_loss(emb, adapter)
+                    w = torch.clamp(CFG['rho'] * adapter.c.mean() / feats.size(0), max=CFG['eta'])
+                    d = w * dl
+                    ec, ed = ua.softmax_entropy(clip_logits), ua.softmax_entropy(d)
+                    wc, wd = 1 / (ec + 1e-3), 1 / (ed + 1e-3)
+                    wc = wc / (wc + wd)
+                    wd = wd / (wc + wd)
+                    final = wc * clip_logits + wd * d
+                else:
+                    adapter.update()
+                    w = torch.clamp(CFG['rho'] * adapter.c.mean() / feats.size(0), max=CFG['eta'])
+                    final = (clip_logits + w * dl).float()
+                finals.append(final), clips.append(clip_logits), dls.append(dl.float())
+        extra = dict(residual=res.detach()) if inp["res_learning"] else {}
+        save(name, inp, final_logits=torch.cat(finals), clip_logits=torch.cat(clips), dota_logits=torch.cat(dls),
+             pred=torch.cat(finals).argmax(1).to(torch.int32), **extra)
+
+
 def main():
     if not R.available():
         sys.exit("reference not found at " + R.REF_ROOT)
@@ -189,6 +277,7 @@ def main():
     print("mode-dota"), mode_dota_goldens()
     print("dota"), dota_goldens()
     print("alignment"), alignment_goldens()
+    print("end-to-end"), e2e_goldens()
 
 
 if __name__ == "__main__":

@@ -57,9 +57,53 @@ def build(verbose: bool = False) -> str:
     return LIB_PATH
 
 
-def lib() -> C.CDLL:
+class _TimedLib:
+    """Proxy around the CDLL that brackets every kernel entry point with CUDA events (profiling aid for bench.py)."""
+
+    def __init__(self, handle):
+        self._h = handle
+        self.records = {}
+
+    def __getattr__(self, name):
+        fn = getattr(self._h, name)
+        if not name.startswith("ua_") or name in ("ua_last_error", "ua_launch_count", "ua_reset_launch_count",
+                                                  "ua_abi_version", "ua_set_tuning"):
+            return fn
+
+        def timed(*args):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            rc = fn(*args)
+            e.record()
+            self.records.setdefault(name, []).append((s, e))
+            return rc
+
+        return timed
+
+    def summary(self):
+        """name -> (calls, total_us, mean_us); call after a synchronize."""
+        out = {}
+        for name, evs in self.records.items():
+            us = [s.elapsed_time(e) * 1e3 for s, e in evs]
+            out[name] = (len(us), sum(us), sum(us) / len(us))
+        return out
+
+
+_timed = None
+
+
+def enable_kernel_timing(flag: bool = True):
+    """Route calls through the event-timing proxy (eager mode only; not usable under CUDA-graph capture)."""
+    global _timed
+    _timed = _TimedLib(lib()) if flag else None
+    return _timed
+
+
+def lib():
     """The loaded library. Fails loudly when it has not been built: no other implementation exists."""
     global _lib
+    if _timed is not None:
+        return _timed
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             raise UaError(

@@ -176,12 +176,15 @@ class _SetAbstraction(nn.Module):
             self.mlp_bns.append(nn.BatchNorm2d(out))
             last = out
         self.next_start_idx = None
+        self.device_rng = False
 
     def forward(self, xyz, points):
         """xyz (B,3,N), points (B,D,N) -> new_xyz (B,3,S), features (B,C,S)."""
         xyz_t = xyz.permute(0, 2, 1).contiguous()
         pts_t = points.permute(0, 2, 1).contiguous() if points is not None else None
         start, self.next_start_idx = self.next_start_idx, None
+        if start is None and self.device_rng:
+            start = torch.randint(0, xyz_t.shape[1], (xyz_t.shape[0],), dtype=torch.long, device=xyz_t.device)
         new_xyz, new_points = tok.sample_and_group(self.npoint, self.radius, self.nsample, xyz_t, pts_t, start_idx=start)
         h = new_points.permute(0, 3, 2, 1)           # (B, C+D, nsample, S)
         for conv, bn in zip(self.mlp_convs, self.mlp_bns):
@@ -243,3 +246,10 @@ def build_encoder(vlm3d: str, seed: int = 0, device='cuda', small: bool = False)
     else:
         raise ValueError(f"unknown vlm3d {vlm3d!r}")
     return m.to(device).float().eval()
+
+
+def set_device_rng(model: nn.Module, flag: bool = True) -> None:
+    """Draw FPS start indices on the device generator (graph-capturable) instead of the CPU one (reference order)."""
+    for mod in model.modules():
+        if hasattr(mod, 'device_rng'):
+            mod.device_rng = flag

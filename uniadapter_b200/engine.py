@@ -1,0 +1,198 @@
+"""Lock-step multi-stream engine: S independent corruption streams adapted side by side on one GPU.
+
+The reference adapts one sample at a time, which leaves a B200 almost idle (the per-sample step is a chain of
+latency-bound launches). Corruption streams are independent (fresh adapter per stream, Uni_Adapter.py:328-339), so
+this engine advances S of them together: one tokenizer launch over S clouds, one encoder forward at batch S, one head
+launch with S text matrices, one MODE-DOTA launch over the stacked state [S,K,M,D], one fusion launch. All buffers
+are static and the no-grad part of the step is captured into a CUDA graph; inputs arrive from pinned host memory.
+
+Per-stream semantics are exactly those of ``adapter.test_zeroshot_3d_core`` at batch 1 (the parity test runs both).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from .dota_mixture import init_state
+from .fusion import fuse_logits
+from .head import zero_shot_head
+from .residual import alignment_loss_from_matrix, gemm_operands, likelihood_matrix_gemm
+
+
+class MultiStreamModeDota:
+    """S MODE-DOTA adapters with stacked state: mu,var (S,K,M,D); pi,c (S,K,M); class_counts (S,K)."""
+
+    def __init__(self, cfg, D, K, text, M, S, device):
+        self.S, self.K, self.M, self.D = S, K, M, D
+        self.epsilon = cfg.get('epsilon', 0.001)
+        self.device = torch.device(device)
+        text = text.to(self.device).float()
+        if text.dim() == 2:
+            text = text.unsqueeze(0).expand(S, -1, -1)
+        states = [init_state(text[s].t().contiguous(), M, cfg.get('sigma', 1.0), self.device) for s in range(S)]
+        self.mu = torch.stack([st[0] for st in states]).contiguous()
+        self.var = torch.stack([st[1] for st in states]).contiguous()
+        self.pi = torch.stack([st[2] for st in states]).contiguous()
+        self.c = torch.stack([st[3] for st in states]).contiguous()
+        self.class_counts = torch.stack([st[4] for st in states]).contiguous()
+        self.t = 0
+
+    def step(self, x_pred, x_fit, gamma_class, out_logits=None):
+        """x_pred (S,Bp,D) | None, x_fit (S,B,D) | None, gamma_class (S,B,K) -> logits (S,Bp,K) | None."""
+        S, K, M, D = self.S, self.K, self.M, self.D
+        Bp = x_pred.shape[1] if x_pred is not None else 0
+        B = x_fit.shape[1] if x_fit is not None else 0
+        if Bp and out_logits is None:
+            out_logits = torch.empty((S, Bp, K), dtype=torch.float32, device=self.device)
+        rc = _lib.lib().ua_modedota_step_f32(
+            _lib.ptr(x_pred), Bp, _lib.ptr(x_fit), _lib.ptr(gamma_class), B, K, 0, _lib.ptr(self.mu), _lib.ptr(self.var),
+            _lib.ptr(self.pi), _lib.ptr(self.c), _lib.ptr(self.class_counts), S, K, M, D, float(self.epsilon),
+            _lib.ptr(out_logits), K, 0, _lib.stream_ptr())
+        _lib.check(rc, "ua_modedota_step_f32")
+        self.t += B
+        return out_logits
+
+
+class StreamEngine:
+    """One adaptation step for S streams per call to :meth:`step`.
+
+    encoder: a module from ``encoders.build_encoder`` (tokenizer inside); text: (K,D) unit rows shared by the
+    streams at start. ``res_learning`` keeps one residual matrix and one Adam state per stream.
+    """
+
+    def __init__(self, encoder, vlm3d, text, num_streams, npoints, cfg, mode_M=8, res_learning=True, device='cuda',
+                 use_graph=True, colored=False, seed=42):
+        self.dev = torch.device(device)
+        self.encoder, self.vlm3d = encoder, vlm3d
+        self.S, self.N = num_streams, npoints
+        self.cfg, self.M = cfg, mode_M
+        self.text0 = text.to(self.dev).float().contiguous()
+        self.K, self.D = self.text0.shape
+        self.res_learning = res_learning
+        self.use_graph = use_graph
+        self.colored = colored
+        S, N, K, D = self.S, self.N, self.K, self.D
+        self.adapter = MultiStreamModeDota(cfg, D, K, self.text0, mode_M, S, self.dev)
+        # static buffers
+        self.pc = torch.zeros(S, N, 3, device=self.dev)
+        self.rgb = torch.ones(S, N, 3, device=self.dev)
+        self.text = self.text0.unsqueeze(0).repeat(S, 1, 1).contiguous()        # current (normalised) text per stream
+        self.final = torch.zeros(S, K, device=self.dev)
+        self.pred = torch.zeros(S, dtype=torch.int32, device=self.dev)
+        self.dota_logits = torch.zeros(S, 1, K, device=self.dev)
+        torch.cuda.manual_seed(seed)
+        from .encoders import set_device_rng
+        set_device_rng(encoder, True)
+        self.step_idx = 0
+        self.graph = None
+        self.inject = None      # parity harness: dict(start, start_aug, noise) for the next eager step
+        if res_learning:
+            self.residuals = torch.zeros(S, K, D, device=self.dev, requires_grad=True)
+            self.optimizer = torch.optim.Adam([self.residuals], lr=0.001, capturable=use_graph)
+        self._host_out = torch.empty(S, K, dtype=torch.float32).pin_memory() if self.dev.type == 'cuda' else None
+
+    # ---- pieces of the step ------------------------------------------------------------------------------------
+    def _encode(self, pc):
+        if self.vlm3d == 'uni3d':
+            return self.encoder.encode_pc(torch.cat((pc, self.rgb), dim=-1))
+        if self.vlm3d == 'ulip':
+            return self.encoder(pc)
+        return self.encoder(pc, torch.cat((pc, self.rgb), dim=-1))
+
+    def _set_start(self, start):
+        if start is not None:
+            for mod in self.encoder.modules():
+                if hasattr(mod, 'next_start_idx'):
+                    mod.next_start_idx = start
+
+    @torch.no_grad()
+    def _adapt(self):
+        """Tokenizer + encoder (x2), head, cache predict+fit, fit on the augmented view, fusion."""
+        S, K = self.S, self.K
+        inj = self.inject or {}
+        self._set_start(inj.get('start'))
+        feats, clip_logits, _, prob, _ = zero_shot_head(self._encode(self.pc), self.text)
+        x_fit = feats.unsqueeze(1)                                     # (S,1,D): batch 1 per stream
+        x_pred = x_fit.half().float()                                  # Uni_Adapter.py:416 rounds through fp16
+        self.adapter.step(x_pred, x_fit, prob.unsqueeze(1), self.dota_logits)
+        noise = inj['noise'] if 'noise' in inj else torch.randn_like(self.pc)
+        pc_aug = self.pc + 0.05 * noise                                 # Uni_Adapter.py:420-421
+        self._set_start(inj.get('start_aug'))
+        feats_aug, _, _, _, _ = zero_shot_head(self._encode(pc_aug), self.text)
+        self.adapter.step(None, feats_aug.unsqueeze(1), prob.unsqueeze(1))
+        self._clip_logits = clip_logits
+
+    @torch.no_grad()
+    def _fuse(self):
+        final, arg, _ = fuse_logits(self._clip_logits, self.dota_logits.view(self.S, self.K), self.adapter.c,
+                                    self.cfg['rho'], self.cfg['eta'], 1, 'mode_dota', per_row_c=True)
+        self.final.copy_(final)
+        self.pred.copy_(arg)
+
+    def _learn_residuals(self):
+        """11 loss evaluations / 10 Adam steps per stream (Uni_Adapter.py:443-476), all streams batched; the
+        likelihood matrix is evaluated in its two-GEMM form (residual.py)."""
+        a = self.adapter
+        with torch.no_grad():
+            ops = gemm_operands(a.mu, a.var, a.pi, a.epsilon)
+        with torch.enable_grad():
+            for it in range(11):
+                emb = self.text0.unsqueeze(0) + self.residuals
+                emb = emb / emb.norm(dim=-1, keepdim=True)
+                loss = alignment_loss_from_matrix(likelihood_matrix_gemm(emb, ops, self.K, self.M)).sum()
+                if it == 10:
+                    break
+                self.optimizer.zero_grad(set_to_none=False)
+                loss.backward()
+                self.optimizer.step()
+        with torch.no_grad():
+            self.text.copy_(F.normalize(self.text0.unsqueeze(0) + self.residuals, dim=-1))
+
+    def _step_body(self, learn: bool):
+        self._adapt()
+        if learn:
+            self._learn_residuals()
+        self._fuse()
+
+    # ---- public ------------------------------------------------------------------------------------------------
+    def _run(self):
+        learn = self.res_learning and self.step_idx > 0
+        if self.use_graph and self.step_idx >= 2:
+            if self.graph is None:
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph):
+                    self._step_body(learn)
+            self.graph.replay()
+        else:
+            self._step_body(learn)
+        self.step_idx += 1
+
+    def step(self, pc_host: torch.Tensor, rgb_host: torch.Tensor | None = None, read_back: bool = True):
+        """End-to-end step: pc_host (S,N,3) pinned host tensor -> (final_logits (S,K) pinned host, pred (S,) device).
+        The host->device copy of the clouds and the device->host read of the fused logits are part of the step."""
+        self.pc.copy_(pc_host, non_blocking=True)
+        if rgb_host is not None:
+            self.rgb.copy_(rgb_host, non_blocking=True)
+        self._run()
+        if read_back:
+            self._host_out.copy_(self.final, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return self._host_out, self.pred
+        return self.final, self.pred
+
+    def step_device(self, pc_dev: torch.Tensor):
+        """Same step with the clouds already resident in HBM; results stay on the device."""
+        self.pc.copy_(pc_dev)
+        self._run()
+        return self.final, self.pred
+
+    def launches_per_step(self) -> int:
+        """Kernel launches of libua_b200.so in one (eager) step, counted by the library itself."""
+        was_graph, self.use_graph = self.use_graph, False
+        _lib.reset_launch_count()
+        self._run()
+        torch.cuda.synchronize()
+        n = _lib.launch_count()
+        self.use_graph = was_graph
+        return n

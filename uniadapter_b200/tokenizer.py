@@ -190,12 +190,16 @@ class Group(nn.Module):
     """Uni3D / ULIP group divider. ``forward(xyz)`` (ULIP, dvae.py:159-181) returns (neighborhood, center);
     ``forward(xyz, color)`` (Uni3D, point_encoder.py:99-127) returns (neighborhood, center, features)."""
 
-    def __init__(self, num_group: int, group_size: int, random_start: bool = False, skip_small_norm: bool = False):
+    def __init__(self, num_group: int, group_size: int, random_start: bool = False, skip_small_norm: bool = False,
+                 device_rng: bool = False):
         super().__init__()
         self.num_group = num_group
         self.group_size = group_size
         self.random_start = random_start      # True: ULIP (torch.randint start); False: Uni3D (pointnet2, start 0)
         self.skip_small_norm = skip_small_norm
+        # False: draw the start on the global CPU generator exactly like the reference (misc.py:52);
+        # True: draw it on the device generator (no host round-trip: required inside CUDA graphs)
+        self.device_rng = device_rng
         self.next_start_idx: torch.Tensor | None = None  # one-shot override used by parity harnesses
 
     def forward(self, xyz: torch.Tensor, color: torch.Tensor | None = None):
@@ -204,7 +208,7 @@ class Group(nn.Module):
         if self.next_start_idx is not None:
             start, self.next_start_idx = self.next_start_idx, None
         elif self.random_start:
-            start = torch.randint(0, N, (B,), dtype=torch.long)
+            start = torch.randint(0, N, (B,), dtype=torch.long, device=xyz.device if self.device_rng else 'cpu')
         _, center = fps_sample(xyz, self.num_group, start, skip_small_norm=self.skip_small_norm, want_idx=False)
         _, neighborhood, features = knn_group(xyz, center, self.group_size, color)
         if color is None:
