@@ -236,3 +236,42 @@ def test_fuse_kernel_vs_oracle(cuda_device):
         final2, _, _ = ua.fuse_logits(cu(clip, cuda_device), cu(dota, cuda_device), None, 0.02, 0.1, 1, 'mode_dota',
                                       c_sum=float(c.sum(dtype=np.float64)), c_count=c.size)
         np.testing.assert_allclose(final2.cpu().numpy(), final.cpu().numpy(), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("P_", [2, 4, 8])
+def test_class_sharded_cache_emulated_ranks(P_, cuda_device):
+    """cfg 4 partitioning on one GPU: P shard objects (one per emulated rank) + an in-process gather must reproduce
+    the unsharded CUDA adapter (the real collective is exercised with gloo on the CPU and NCCL in bench runs)."""
+    import uniadapter_b200 as ua
+    from uniadapter_b200 import parallel as PP
+    from oracle import synth
+    K, M, D, T = 203, 8, 256, 4          # 203 classes: uneven shards for every P
+    cfg = cases.CFG
+    dev = cuda_device
+    text = torch.from_numpy(synth.unit_rows(K, D, 7)).to(dev)
+    x, xa, _ = synth.features(T, 1, D, text.cpu().numpy(), 8)
+    x, xa = cu(x * np.float32(2.5), dev), cu(xa * np.float32(1.5), dev)
+    shards = [PP.ShardedModeDota(cfg, text, M, lambda ts: PP.CudaShardOps(cfg, D, ts, M, dev), rank=r, world=P_,
+                                 gather_fn=lambda self: None) for r in range(P_)]
+    full = ua.DOTA_mix(cfg, D, K, text.t().contiguous(), num_modes=M, device=dev)
+    for t in range(T):
+        for sh in shards:
+            sh.local_logits(x[t])
+        gathered = torch.stack([sh.send for sh in shards])          # what all_gather_into_tensor delivers
+        outs = []
+        for sh in shards:
+            sh.recv.copy_(gathered)
+            outs.append(sh.finish(xa[t]))
+        feats, clip_logits, _, prob, _ = ua.zero_shot_head(x[t], text)
+        dl = full.predict_then_fit(feats.mean(0, keepdim=True).half(), feats, prob)
+        full.fit(ua.zero_shot_head(xa[t], text)[0], prob)
+        final, arg, _ = ua.fuse_logits(clip_logits, dl, full.c, cfg['rho'], cfg['eta'], 1, 'mode_dota')
+        for o in outs:
+            assert o.pred == int(arg[0])
+            np.testing.assert_allclose(o.clip_logits.cpu().numpy(), clip_logits.cpu().numpy(), rtol=1e-6, atol=1e-6)
+            np.testing.assert_allclose(o.dota_logits.cpu().numpy(), dl.cpu().numpy(), rtol=1e-6, atol=1e-5)
+            np.testing.assert_allclose(o.final_logits.cpu().numpy(), final.cpu().numpy(), rtol=1e-5, atol=1e-5)
+    for sh in shards:
+        assert torch.equal(sh.ops.cache.mu[0], full.mu[sh.k_lo:sh.k_hi])
+        assert torch.equal(sh.ops.cache.var[0], full.var[sh.k_lo:sh.k_hi])
+        assert torch.equal(sh.ops.cache.c[0], full.c[sh.k_lo:sh.k_hi])
