@@ -113,7 +113,8 @@ int ua_head_f32(const float* x, int B, int D, const float* text, int num_text, i
  * reference's single adapter object; S > 1 runs S adapters in lock-step in one launch).
  * One launch evaluates  predict(x_pred) on the CURRENT state (if x_pred != NULL) and then applies
  * fit(x_fit, gamma_class) in place (if x_fit != NULL); each class's (M,D) state tile is read from HBM once
- * and written once (TMA bulk copies through a two-stage shared-memory ring).
+ * and written once (TMA bulk loads through a shared-memory ring; register-resident M-step and direct warp stores
+ * on the single-sample path Bp <= 1, B <= 1, D % 128 == 0; bulk stores on the general path).
  *   x_pred [S,Bp,D] -> out_logits [S,Bp,ldo] written at columns [k_out_offset, k_out_offset+K)
  *   x_fit [S,B,D], gamma_class [S,B,ldg] read at columns [k_gamma_offset, k_gamma_offset+K)
  * (the offsets / leading dimensions let a class-sharded rank use the full-width logits / prob_map buffers).

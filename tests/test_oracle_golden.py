@@ -83,20 +83,42 @@ def logit_atol(D):
     return 1e-4 * D
 
 
-def state_tol(inp):
+def state_tol(inp, name=None):
     """fp32 relative 1e-4 (north star) plus an absolute floor. The floor exists because the log-likelihoods are
     O(1e3..1e4) in fp32 (ulp 2e-4..1e-3), so the mode responsibilities exp(ll - lse) of the REFERENCE ITSELF carry
-    ~1e-3 relative noise; it shows up in weak modes and grows with the number of samples per fit."""
+    ~1e-3 relative noise; it shows up in weak modes and grows with the number of samples per fit.
+
+    With ``name`` (a golden MODE-DOTA case) the floor additionally covers the reference's measured sensitivity to the
+    fp32 summation order on that very stream (3 x the distance between the oracle and its exactly-summed twin,
+    ``oracle.adapters.ModeDotaExactSum``): an implementation that sums over D in another order than torch's CPU
+    kernels (the CUDA path) cannot be closer to the golden than the golden is to its own re-association."""
     B, D = inp["B"], inp["D"]
     # mu: 2e-4 of the typical magnitude 1/sqrt(D) of a unit-norm feature component
-    return dict(c=2e-4 if B == 1 else 2e-5 * B, pi=5e-5 if B == 1 else 2e-6 * B,
-                mu=max(2e-4 / D ** 0.5, 1e-7 * B if B > 1 else 0.0))
+    tol = dict(c=2e-4 if B == 1 else 2e-5 * B, pi=5e-5 if B == 1 else 2e-6 * B,
+               mu=max(2e-4 / D ** 0.5, 1e-7 * B if B > 1 else 0.0), var=VAR_ATOL)
+    if name is not None:
+        sens = summation_sensitivity(name)
+        tol = {k: v + 3.0 * sens[k] for k, v in tol.items()}
+    return tol
 
 
-def run_mode_dota_oracle(inp):
+_SENS = {}
+
+
+def summation_sensitivity(name):
+    """max |state(oracle) - state(exactly-summed oracle)| after the stream of golden case ``name``."""
+    if name not in _SENS:
+        inp = cases.modedota_inputs(name)
+        a = run_mode_dota_oracle(inp)[0]
+        b = run_mode_dota_oracle(inp, cls=A.ModeDotaExactSum)[0]
+        _SENS[name] = {k: float(np.abs(getattr(a, k) - getattr(b, k)).max()) for k in ("mu", "var", "c", "pi")}
+    return _SENS[name]
+
+
+def run_mode_dota_oracle(inp, cls=A.ModeDota):
     cfg = cases.CFG
     text, x, xa = inp["text"], inp["x"], inp["x_aug"]
-    model = A.ModeDota(cfg, inp["D"], inp["K"], text.T, inp["M"])
+    model = cls(cfg, inp["D"], inp["K"], text.T, inp["M"])
     dls, finals = [], []
     for t in range(inp["T"]):
         h = A.head(x[t], text)

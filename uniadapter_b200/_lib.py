@@ -115,6 +115,9 @@ def lib():
             fn.restype = res
             fn.argtypes = args
         _lib = handle
+        for kv in filter(None, os.environ.get("UA_TUNING", "").split(",")):     # experiments: "key=value,key=value"
+            key, _, val = kv.partition("=")
+            check(handle.ua_set_tuning(key.strip().encode(), int(val)), f"UA_TUNING {kv}")
     return _lib
 
 

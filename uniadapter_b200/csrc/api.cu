@@ -12,6 +12,9 @@ static std::atomic<int64_t> g_launches{0};
 extern int g_fps_threads;
 extern int g_knn_warps;
 extern int g_modedota_threads;
+extern int g_modedota_v;
+extern int g_modedota_groups;
+extern int g_modedota_logprod;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -44,6 +47,9 @@ extern "C" int ua_set_tuning(const char* key, int value) {
   if (!strcmp(key, "fps_threads")) { ua::g_fps_threads = value; return UA_OK; }
   if (!strcmp(key, "knn_warps")) { ua::g_knn_warps = value; return UA_OK; }
   if (!strcmp(key, "modedota_threads")) { ua::g_modedota_threads = value; return UA_OK; }
+  if (!strcmp(key, "modedota_groups")) { ua::g_modedota_groups = value; return UA_OK; }
+  if (!strcmp(key, "modedota_v")) { ua::g_modedota_v = value; return UA_OK; }
+  if (!strcmp(key, "modedota_logprod")) { ua::g_modedota_logprod = value; return UA_OK; }
   ua::set_error("ua_set_tuning: unknown key '%s'", key);
   return UA_ERR_INVALID_ARG;
 }
