@@ -139,6 +139,32 @@ int ua_fuse_logits_f32(const float* clip_logits, const void* dota_logits, int do
                        float* out_scaled_dota, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Residual text-feature learning
+ * Replaces: Uni_Adapter.py:191-270 (compute_text_alignment_loss, forward + autograd backward) and the inner loop
+ * Uni_Adapter.py:443-476 (zero_grad / backward / Adam.step x10 on text_residuals, torch.optim.Adam defaults).
+ *   text0 [K,D] (text0_stream_stride = 0) or [S,K,D] (= K*D): the fixed initial text features
+ *   residual, adam_m, adam_v [S,K,D] updated in place; adam_t [S] i32 on the device: Adam steps taken so far,
+ *   advanced by `iters` (on the device, so a captured CUDA graph keeps counting)
+ *   mu,var [S,K,M,D], pi [S,K,M]: the MODE-DOTA state (read only)
+ *   out_text [S,K,D] = normalize(text0 + residual) after the updates (the next sample's clip_weights^T)
+ *   out_loss [S,iters] or NULL: the alignment loss before each step
+ *   scratch: ua_residual_scratch_floats(S,K,M,D) floats, 16-byte aligned.
+ * ua_align_loss_grad_f32 evaluates one loss / likelihood matrix [S,K,K] / gradient w.r.t. the residual [S,K,D]
+ * (any of them NULL to skip) without touching the residual; out_emb [S,K,D] receives the normalised embeddings.
+ * Limits: D % 128 == 0, M in {4,8,12,16}, K <= 128.
+ * ---------------------------------------------------------------------------------------- */
+long long ua_residual_scratch_floats(int S, int K, int M, int D);
+int ua_residual_learn_f32(const float* text0, long long text0_stream_stride, float* residual, float* adam_m,
+                          float* adam_v, int32_t* adam_t, const float* mu, const float* var, const float* pi, int S,
+                          int K, int M, int D, float eps, double lr, double beta1, double beta2, double adam_eps,
+                          int iters, float* out_text, float* out_loss, float* scratch, long long scratch_floats,
+                          void* stream);
+int ua_align_loss_grad_f32(const float* text0, long long text0_stream_stride, const float* residual, const float* mu,
+                           const float* var, const float* pi, int S, int K, int M, int D, float eps, float* out_emb,
+                           float* out_loss, float* out_lm, float* out_grad, float* scratch, long long scratch_floats,
+                           void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * DOTA (full covariance)
  * Replaces: dota.py:41-63 (fit), :72-87 (predict). dota.py:66-69 (update: DxD inverse) stays a library call.
  *   fit:  mu [K,D], c [K], Sigma [K,D,D], overall [D,D] updated in place from x [B,D], y [B,K].

@@ -55,6 +55,7 @@ DOTA = {
 ALIGN = {
     "align_k10_m4_d64": (10, 4, 64, 61),
     "align_k40_m8_d512": (40, 8, 512, 62),
+    "align_k15_m4_d128": (15, 4, 128, 63),
 }
 
 

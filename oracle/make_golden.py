@@ -272,12 +272,10 @@ def main():
     if not R.available():
         sys.exit("reference not found at " + R.REF_ROOT)
     torch.set_num_threads(8)
-    print("tokenizer"), tokenizer_goldens()
-    print("head"), head_goldens()
-    print("mode-dota"), mode_dota_goldens()
-    print("dota"), dota_goldens()
-    print("alignment"), alignment_goldens()
-    print("end-to-end"), e2e_goldens()
+    groups = dict(tokenizer=tokenizer_goldens, head=head_goldens, modedota=mode_dota_goldens, dota=dota_goldens,
+                  alignment=alignment_goldens, e2e=e2e_goldens)
+    for name in (sys.argv[1:] or list(groups)):       # python -m oracle.make_golden [group ...]
+        print(name), groups[name]()
 
 
 if __name__ == "__main__":

@@ -179,3 +179,19 @@ def test_dota_oracle_matches_reference(name):
     np.testing.assert_allclose(model.c, gold["c"], rtol=1e-6)
     np.testing.assert_allclose(np.diagonal(model.Sigma, axis1=1, axis2=2), gold["Sigma_diag"], rtol=1e-4, atol=1e-10)
     np.testing.assert_allclose(model.Sigma[0], gold["Sigma_k0"], rtol=1e-4, atol=1e-10)
+
+
+@pytest.mark.parametrize("name", list(cases.ALIGN))
+def test_alignment_loss_and_gradient_oracle_matches_reference(name):
+    """The hand-derived backward of compute_text_alignment_loss (what csrc/residual.cu implements) against the
+    reference's autograd: loss, likelihood matrix and d loss / d residual."""
+    inp = cases.align_inputs(name)
+    gold = load_golden(name, inp)
+    for dtype, rtol in ((np.float64, 5e-4), (np.float32, 5e-4)):
+        loss, lm, grad, _ = A.align_loss_grad(inp["text"], inp["residual"], gold["mu"], gold["var"], gold["pi"],
+                                              cases.CFG['epsilon'], dtype=dtype)
+        np.testing.assert_allclose(lm, gold["likelihood"], rtol=1e-5, atol=1e-4 * inp["D"] ** 0.5)
+        np.testing.assert_allclose(loss, gold["loss"], rtol=1e-5)
+        # the gradient is a difference of O(1) terms scaled by 1/max(LM) ~ 1e-3: compare against its own scale
+        scale = np.abs(gold["grad"]).max()
+        np.testing.assert_allclose(grad, gold["grad"], rtol=rtol, atol=rtol * scale)

@@ -37,6 +37,11 @@ SIGNATURES = {
     "ua_head_f32": (_I, [_P, _I, _I, _P, _I, _I, _F, _P, _P, _P, _P, _P, _P]),
     "ua_modedota_step_f32": (_I, [_P, _I, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _I, _I, _P]),
     "ua_fuse_logits_f32": (_I, [_P, _P, _I, _I, _I, _P, _I, _I, _F, _F, _F, _F, _F, _I, _P, _P, _P, _P]),
+    "ua_residual_scratch_floats": (C.c_longlong, [_I, _I, _I, _I]),
+    "ua_residual_learn_f32": (_I, [_P, C.c_longlong, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, C.c_double,
+                                    C.c_double, C.c_double, C.c_double, _I, _P, _P, _P, C.c_longlong, _P]),
+    "ua_align_loss_grad_f32": (_I, [_P, C.c_longlong, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P,
+                                     C.c_longlong, _P]),
     "ua_dota_fit_f32": (_I, [_P, _P, _I, _P, _P, _P, _P, _I, _I, _P]),
     "ua_dota_predict_f16": (_I, [_P, _I, _P, _P, _I, _I, _P, _P]),
     "ua_dota_regularize_f32": (_I, [_P, _I, _F, _P, _P]),

@@ -12,13 +12,12 @@ import logging
 import os
 
 import torch
-import torch.nn.functional as F
 
 from .dota import DOTA
 from .dota_mixture import DOTA_mix
 from .fusion import fuse_logits
 from .head import get_logits_wrapper
-from .residual import compute_text_alignment_loss
+from .residual import ResidualLearner
 
 
 class AverageMeter:
@@ -82,10 +81,8 @@ def test_zeroshot_3d_core(test_loader, validate_dataset_name, model, clip_model,
     else:
         adapter = DOTA(dota_cfg, D, K, torch.full((D, K), 0.001), device=device)   # Uni_Adapter.py:329-330
         logging.info("Initialized DOTA model.")
-    if res_learning:
-        text_initial = text_features.clone()
-        text_residuals = torch.zeros_like(text_initial, requires_grad=True)
-        residual_optimizer = torch.optim.Adam([text_residuals], lr=0.001)
+    if res_learning:   # text_residuals + Adam(lr 1e-3) of Uni_Adapter.py:346-352, advanced on the device
+        learner = ResidualLearner(text_features, 1, args.mode_M, device, lr=0.001)
 
     stored_times, preds, all_logits = [], [], []
     start_event, end_event = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -97,7 +94,7 @@ def test_zeroshot_3d_core(test_loader, validate_dataset_name, model, clip_model,
         target = torch.as_tensor(target).to(device=device, non_blocking=True)
         feature = torch.cat((pc, rgb), dim=-1)
         if res_learning:
-            clip_weights = F.normalize(text_initial + text_residuals.detach(), dim=1).t()
+            clip_weights = learner.text[0].t()      # normalize(text_initial + text_residuals), Uni_Adapter.py:389-392
         else:
             clip_weights = text_features.t()
 
@@ -120,16 +117,10 @@ def test_zeroshot_3d_core(test_loader, validate_dataset_name, model, clip_model,
             adapter.fit(feats_aug, prob_map)                                        # xnorm is idempotent under :429
             adapter.update()
             if i > 0 and res_learning:
-                with torch.enable_grad():
-                    for it in range(11):                                            # 1 + 10 loss evaluations (:455-476)
-                        emb = text_initial + text_residuals
-                        emb = emb / emb.norm(dim=1, keepdim=True)
-                        alignment_loss, _ = compute_text_alignment_loss(emb, adapter)
-                        if it == 10:
-                            break
-                        residual_optimizer.zero_grad()
-                        alignment_loss.backward()
-                        residual_optimizer.step()
+                # 10 x (zero_grad, backward, Adam.step) of Uni_Adapter.py:455-476 in one library call; the 11th loss
+                # evaluation of the reference changes no state
+                learner.learn(adapter.mu.unsqueeze(0), adapter.var.unsqueeze(0), adapter.pi.unsqueeze(0),
+                              adapter.epsilon, iters=10)
             final_logits, _, _ = fuse_logits(clip_logits, dota_logits, adapter.c, dota_cfg['rho'], dota_cfg['eta'], B,
                                              'mode_dota')
         end_event.record()

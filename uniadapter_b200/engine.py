@@ -11,13 +11,12 @@ Per-stream semantics are exactly those of ``adapter.test_zeroshot_3d_core`` at b
 from __future__ import annotations
 
 import torch
-import torch.nn.functional as F
 
 from . import _lib
 from .dota_mixture import init_state
 from .fusion import fuse_logits
 from .head import zero_shot_head
-from .residual import alignment_loss_from_matrix, gemm_operands, likelihood_matrix_gemm
+from .residual import ResidualLearner
 
 
 class MultiStreamModeDota:
@@ -77,7 +76,12 @@ class StreamEngine:
         # static buffers
         self.pc = torch.zeros(S, N, 3, device=self.dev)
         self.rgb = torch.ones(S, N, 3, device=self.dev)
-        self.text = self.text0.unsqueeze(0).repeat(S, 1, 1).contiguous()        # current (normalised) text per stream
+        if res_learning:   # residuals + Adam state per stream; learner.text = normalize(text0 + residual)
+            self.learner = ResidualLearner(self.text0, S, mode_M, self.dev)
+            self.text = self.learner.text
+            self.residuals = self.learner.residual
+        else:
+            self.text = self.text0.unsqueeze(0).repeat(S, 1, 1).contiguous()    # (normalised) text per stream
         self.final = torch.zeros(S, K, device=self.dev)
         self.pred = torch.zeros(S, dtype=torch.int32, device=self.dev)
         self.dota_logits = torch.zeros(S, 1, K, device=self.dev)
@@ -87,9 +91,6 @@ class StreamEngine:
         self.step_idx = 0
         self.graph = None
         self.inject = None      # parity harness: dict(start, start_aug, noise) for the next eager step
-        if res_learning:
-            self.residuals = torch.zeros(S, K, D, device=self.dev, requires_grad=True)
-            self.optimizer = torch.optim.Adam([self.residuals], lr=0.001, capturable=use_graph)
         self._host_out = torch.empty(S, K, dtype=torch.float32).pin_memory() if self.dev.type == 'cuda' else None
 
     # ---- pieces of the step ------------------------------------------------------------------------------------
@@ -131,23 +132,10 @@ class StreamEngine:
         self.pred.copy_(arg)
 
     def _learn_residuals(self):
-        """11 loss evaluations / 10 Adam steps per stream (Uni_Adapter.py:443-476), all streams batched; the
-        likelihood matrix is evaluated in its two-GEMM form (residual.py)."""
+        """10 alignment-loss backward / Adam rounds per stream (Uni_Adapter.py:443-476; the 11th loss evaluation of
+        the reference has no effect on any state), all streams in one library call (csrc/residual.cu)."""
         a = self.adapter
-        with torch.no_grad():
-            ops = gemm_operands(a.mu, a.var, a.pi, a.epsilon)
-        with torch.enable_grad():
-            for it in range(11):
-                emb = self.text0.unsqueeze(0) + self.residuals
-                emb = emb / emb.norm(dim=-1, keepdim=True)
-                loss = alignment_loss_from_matrix(likelihood_matrix_gemm(emb, ops, self.K, self.M)).sum()
-                if it == 10:
-                    break
-                self.optimizer.zero_grad(set_to_none=False)
-                loss.backward()
-                self.optimizer.step()
-        with torch.no_grad():
-            self.text.copy_(F.normalize(self.text0.unsqueeze(0) + self.residuals, dim=-1))
+        self.learner.learn(a.mu, a.var, a.pi, a.epsilon, iters=10)
 
     def _step_body(self, learn: bool):
         self._adapt()
