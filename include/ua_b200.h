@@ -165,6 +165,23 @@ int ua_align_loss_grad_f32(const float* text0, long long text0_stream_stride, co
                            void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * fp32-accurate GEMM on tcgen05 tensor cores (3xTF32), the dense contraction of the path:
+ *   C[M,N] = epilogue(A[M,K] . W[N,K]^T)   — the layout of nn.Linear / 1x1 Conv1d weights
+ * Replaces: the zero-shot head contraction at batch >= 64 (Uni_Adapter.py:61-62), the mini-PointNet group encoder's
+ * 1x1 convolutions (models/ulip/pointbert/dvae.py:201-215, models/point_encoder.py:145-159).
+ * Operands come as (hi, lo) pairs: hi = tf32(x), lo = x - hi (ua_split_tf32_f32, or the OUT_SPLIT epilogue of the
+ * producing GEMM). Epilogue: + bias[N], + group_bias[row/32, N], ReLU, then any of
+ *   out [M,ldo] fp32;  (out_hi, out_lo) [M,ldo];  gmax [M/32, N] = max over each 32 consecutive rows (one point
+ *   group; needs M % 32 == 0) with an optional (gmax_hi, gmax_lo) copy.
+ * Limits: N % 128 == 0, K % 32 == 0, 16-byte aligned operands, lda/ldw/ldo multiples of 4.
+ * ---------------------------------------------------------------------------------------- */
+int ua_split_tf32_f32(const float* x, float* hi, float* lo, long long n, void* stream);
+int ua_gemm_tf32x3_f32(const float* a_hi, const float* a_lo, long long lda, const float* w_hi, const float* w_lo,
+                       long long ldw, int M, int N, int K, const float* bias, const float* group_bias, int relu,
+                       float* out, float* out_hi, float* out_lo, long long ldo, float* gmax, float* gmax_hi,
+                       float* gmax_lo, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * DOTA (full covariance)
  * Replaces: dota.py:41-63 (fit), :72-87 (predict). dota.py:66-69 (update: DxD inverse) stays a library call.
  *   fit:  mu [K,D], c [K], Sigma [K,D,D], overall [D,D] updated in place from x [B,D], y [B,K].

@@ -42,6 +42,9 @@ SIGNATURES = {
                                     C.c_double, C.c_double, C.c_double, _I, _P, _P, _P, C.c_longlong, _P]),
     "ua_align_loss_grad_f32": (_I, [_P, C.c_longlong, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P,
                                      C.c_longlong, _P]),
+    "ua_split_tf32_f32": (_I, [_P, _P, _P, C.c_longlong, _P]),
+    "ua_gemm_tf32x3_f32": (_I, [_P, _P, C.c_longlong, _P, _P, C.c_longlong, _I, _I, _I, _P, _P, _I, _P, _P, _P,
+                                 C.c_longlong, _P, _P, _P, _P]),
     "ua_dota_fit_f32": (_I, [_P, _P, _I, _P, _P, _P, _P, _I, _I, _P]),
     "ua_dota_predict_f16": (_I, [_P, _I, _P, _P, _I, _I, _P, _P]),
     "ua_dota_regularize_f32": (_I, [_P, _I, _F, _P, _P]),

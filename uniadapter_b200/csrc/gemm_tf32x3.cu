@@ -1,0 +1,439 @@
+// fp32-accurate GEMM on the 5th-generation tensor cores (tcgen05, kind::tf32) for sm_100a.
+//
+//   C[M,N] = epilogue(A[M,K] . W[N,K]^T)          A, W row-major with K contiguous ("K-major", nn.Linear / 1x1-conv layout)
+//
+// fp32 accuracy comes from the 3xTF32 split: every operand is stored as a pair (hi, lo) with hi = tf32(x) (low 13
+// mantissa bits zero, so the tensor core reads it exactly) and lo = x - hi (exact in fp32); the kernel accumulates
+//   A_lo.W_hi + A_hi.W_lo + A_hi.W_hi   in the fp32 TMEM accumulator (the dropped lo.lo term is 2^-22 relative).
+// Producers write their outputs directly as (hi, lo) pairs (OUT_SPLIT epilogue), so a chain of GEMMs never runs a
+// separate split pass.
+//
+// Structure (one CTA per SM, persistent over 128 x BN output tiles, warp-specialised):
+//   warp 0     TMA producer: cp.async.bulk.tensor (128B swizzle) of A_hi, A_lo [128 x 32] and W_hi, W_lo [BN x 32]
+//              per k-block into a multi-stage shared-memory ring (full/empty mbarriers)
+//   warp 1     TMEM allocation; one elected lane issues tcgen05.mma (M=128, N=BN, K=8 per instruction, 12 per
+//              k-block), tcgen05.commit releases the smem stage / publishes the accumulator
+//   warps 2-5  epilogue: tcgen05.ld of the accumulator (one row per thread, 32 columns per load), bias / per-row-group
+//              bias / ReLU, then any of: fp32 store, (hi, lo) store, max over each group of 32 consecutive rows
+//              (= one warp's TMEM lanes: the max over the 32 points of a point group)
+//   two accumulator stages in TMEM (2 x BN <= 512 columns): the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <cuda.h>
+#include "common.cuh"
+
+namespace ua {
+namespace {
+
+constexpr int kBM = 128;         // rows per tile (UMMA M)
+constexpr int kBK = 32;          // fp32 elements per k-block = 128 bytes = one swizzle-128B row
+constexpr int kUmmaK = 8;        // tf32 elements per tcgen05.mma
+constexpr int kGemmThreads = 192;
+
+struct GemmParams {
+  int M, N, K;
+  const float* bias;        // [N] or null
+  const float* group_bias;  // [ceil(M/32), N] or null: added to every row of a 32-row group
+  int relu;
+  float* out;               // [M, ldo] fp32 or null
+  float* out_hi;            // [M, ldo] or null (with out_lo)
+  float* out_lo;
+  long long ldo;
+  float* gmax;              // [M/32, N] fp32 or null: max over each group of 32 consecutive rows
+  float* gmax_hi;           // optional (hi, lo) copy of gmax
+  float* gmax_lo;
+};
+
+// ---- PTX wrappers ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .b32 rx;\n"
+      ".reg .pred px;\n"
+      "elect.sync rx|px, %1;\n"
+      "@px mov.s32 %0, 1;\n"
+      "}\n"
+      : "+r"(pred)
+      : "r"(0xFFFFFFFFu));
+  return pred;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] . B[smem desc]^T, tf32 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// the mbarrier receives one arrival when every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// 32 lanes x 32 consecutive 32-bit columns: thread t of the warp receives row (lane base + t)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor of a K-major tile whose rows are 128 bytes, 128B-swizzled (what the TMA box
+// [32 fp32 x rows] with CU_TENSOR_MAP_SWIZZLE_128B writes): 8-row atoms of 1024 bytes (stride byte offset),
+// descriptor version 1 (sm_100), layout type 2 (SWIZZLE_128B). Addresses and offsets are in units of 16 bytes.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);       // start address        bits [0,14)
+  d |= (uint64_t)1 << 16;                            // leading byte offset  bits [16,30) (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset   bits [32,46)
+  d |= (uint64_t)1 << 46;                            // version              bits [46,48)
+  d |= (uint64_t)2 << 61;                            // layout type          bits [61,64)
+  return d;
+}
+// Instruction descriptor: D fp32, A/B tf32, both K-major, dense; N >> 3 at [17,23), M >> 4 at [24,29).
+__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ float tf32_round(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+// order-preserving float <-> int map for REDUX max
+__device__ __forceinline__ int float_to_sortable(float f) {
+  const int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float sortable_to_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+template <int BN, int STAGES>
+struct SmemLayout {
+  static constexpr int kABytes = kBM * kBK * 4;       // 16 KB
+  static constexpr int kBBytes = BN * kBK * 4;
+  static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+  static constexpr int kTotal = STAGES * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+    gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                       const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+                       const GemmParams p) {
+  using L = SmemLayout<BN, STAGES>;
+  extern __shared__ unsigned char s_raw[];
+  // 128B-swizzled tiles need 1024-byte alignment
+  unsigned char* s_tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(s_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* s_full = reinterpret_cast<uint64_t*>(s_tiles + STAGES * L::kStageBytes);   // [STAGES]
+  uint64_t* s_empty = s_full + STAGES;                                                   // [STAGES]
+  uint64_t* s_tfull = s_empty + STAGES;                                                  // [2]
+  uint64_t* s_tempty = s_tfull + 2;                                                      // [2]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (p.M + kBM - 1) / kBM, n_tiles = p.N / BN, k_blocks = p.K / kBK;
+  const int total_tiles = m_tiles * n_tiles;
+
+  if (warp == 0 && elect_one()) {
+    prefetch_tmap(&map_a_hi), prefetch_tmap(&map_a_lo), prefetch_tmap(&map_w_hi), prefetch_tmap(&map_w_lo);
+    for (int i = 0; i < STAGES; ++i) mbar_init(&s_full[i], 1), mbar_init(&s_empty[i], 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&s_tfull[i], 1), mbar_init(&s_tempty[i], 4);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(s_tmem, 2 * BN);     // 2 accumulator stages of BN fp32 columns (power of two >= 32)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int m_idx = (t / n_tiles) * kBM, n_idx = (t % n_tiles) * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&s_empty[stage], phase ^ 1u);
+          unsigned char* st = s_tiles + stage * L::kStageBytes;
+          mbar_expect_tx(&s_full[stage], (uint32_t)L::kStageBytes);
+          tma_load_2d(st, &map_a_hi, &s_full[stage], kb * kBK, m_idx);
+          tma_load_2d(st + L::kABytes, &map_a_lo, &s_full[stage], kb * kBK, m_idx);
+          tma_load_2d(st + 2 * L::kABytes, &map_w_hi, &s_full[stage], kb * kBK, n_idx);
+          tma_load_2d(st + 2 * L::kABytes + L::kBBytes, &map_w_lo, &s_full[stage], kb * kBK, n_idx);
+          if (++stage == STAGES) stage = 0, phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc(kBM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        mbar_wait(&s_tempty[acc], acc_phase ^ 1u);       // the epilogue has drained this accumulator stage
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&s_full[stage], phase);
+          tc_fence_after();
+          const uint32_t st = smem_u32(s_tiles + stage * L::kStageBytes);
+          const uint64_t a_hi = make_smem_desc(st), a_lo = make_smem_desc(st + L::kABytes);
+          const uint64_t w_hi = make_smem_desc(st + 2 * L::kABytes);
+          const uint64_t w_lo = make_smem_desc(st + 2 * L::kABytes + L::kBBytes);
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k) {
+            const uint64_t koff = (uint64_t)((k * kUmmaK * 4) >> 4);   // 32 bytes per step inside the swizzled row
+            umma_tf32(d_tmem, a_lo + koff, w_hi + koff, idesc, (kb | k) != 0);
+            umma_tf32(d_tmem, a_hi + koff, w_lo + koff, idesc, 1u);
+            umma_tf32(d_tmem, a_hi + koff, w_hi + koff, idesc, 1u);
+          }
+          umma_commit(&s_empty[stage]);                  // frees the smem stage once these MMAs have read it
+          if (kb == k_blocks - 1) umma_commit(&s_tfull[acc]);
+          if (++stage == STAGES) stage = 0, phase ^= 1u;
+        }
+        if (++acc == 2) acc = 0, acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ===== epilogue warps (2..5): TMEM lanes 32*(warp % 4) .. +31 =====
+    const int quarter = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int m_idx = (t / n_tiles) * kBM, n_idx = (t % n_tiles) * BN;
+      const int row = m_idx + quarter * 32 + lane;
+      const bool row_ok = row < p.M;
+      const int group = (m_idx + quarter * 32) >> 5;       // 32-row group of this warp
+      mbar_wait(&s_tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        tmem_ld_32x32(t_row + (uint32_t)c0, v);
+        const int col = n_idx + c0;
+        if (p.bias) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col + i));
+            v[i] += b.x, v[i + 1] += b.y, v[i + 2] += b.z, v[i + 3] += b.w;
+          }
+        }
+        if (p.group_bias) {
+          const float* gb = p.group_bias + (size_t)group * p.N + col;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(gb + i));
+            v[i] += b.x, v[i + 1] += b.y, v[i + 2] += b.z, v[i + 3] += b.w;
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        if (p.out && row_ok) {
+          float4* o = reinterpret_cast<float4*>(p.out + (size_t)row * p.ldo + col);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+        if (p.out_hi && row_ok) {
+          float4* oh = reinterpret_cast<float4*>(p.out_hi + (size_t)row * p.ldo + col);
+          float4* ol = reinterpret_cast<float4*>(p.out_lo + (size_t)row * p.ldo + col);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 h, l;
+            h.x = tf32_round(v[4 * i]), l.x = v[4 * i] - h.x;
+            h.y = tf32_round(v[4 * i + 1]), l.y = v[4 * i + 1] - h.y;
+            h.z = tf32_round(v[4 * i + 2]), l.z = v[4 * i + 2] - h.z;
+            h.w = tf32_round(v[4 * i + 3]), l.w = v[4 * i + 3] - h.w;
+            oh[i] = h, ol[i] = l;
+          }
+        }
+        if (p.gmax) {
+          // max over the warp's 32 rows (one point group), one REDUX per column; lane i keeps column i
+          float mine = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int m = __reduce_max_sync(kFullMask, float_to_sortable(row_ok ? v[i] : -INFINITY));
+            if (lane == i) mine = sortable_to_float(m);
+          }
+          if (m_idx + quarter * 32 < p.M) {
+            const size_t o = (size_t)group * p.N + col + lane;
+            p.gmax[o] = mine;
+            if (p.gmax_hi) {
+              const float h = tf32_round(mine);
+              p.gmax_hi[o] = h, p.gmax_lo[o] = mine - h;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_tempty[acc]);
+      if (++acc == 2) acc = 0, acc_phase ^= 1u;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
+}
+
+// hi = tf32(x) (round to nearest, low 13 bits zero), lo = x - hi
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi,
+                                                         float* __restrict__ lo, long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    float4 h, l;
+    h.x = tf32_round(v.x), l.x = v.x - h.x;
+    h.y = tf32_round(v.y), l.y = v.y - h.y;
+    h.z = tf32_round(v.z), l.z = v.z - h.z;
+    h.w = tf32_round(v.w), l.w = v.w - h.w;
+    reinterpret_cast<float4*>(hi)[i] = h;
+    reinterpret_cast<float4*>(lo)[i] = l;
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor [rows, cols] with row pitch ld (elements), box [box_rows x 32 columns], 128B swizzle, zero fill
+int make_map(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("ua_gemm_tf32x3_f32: cuTensorMapEncodeTiled is not available from the driver");
+    return UA_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("ua_gemm_tf32x3_f32: cuTensorMapEncodeTiled failed with %d (base %p rows %lld cols %lld ld %lld)", (int)r,
+              (const void*)base, rows, cols, ld);
+    return UA_ERR_CUDA;
+  }
+  return UA_OK;
+}
+
+template <int BN, int STAGES>
+int launch_gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo,
+                const GemmParams& p, cudaStream_t st) {
+  using L = SmemLayout<BN, STAGES>;
+  auto kern = gemm_tf32x3_kernel<BN, STAGES>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+  if (e != cudaSuccess) {
+    set_error("ua_gemm_tf32x3_f32: cudaFuncSetAttribute(%d B): %s", L::kTotal, cudaGetErrorString(e));
+    return UA_ERR_CUDA;
+  }
+  const int tiles = ((p.M + kBM - 1) / kBM) * (p.N / BN);
+  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  kern<<<grid, kGemmThreads, L::kTotal, st>>>(a_hi, a_lo, w_hi, w_lo, p);
+  return check_launch("ua_gemm_tf32x3_f32");
+}
+
+}  // namespace
+}  // namespace ua
+
+extern "C" int ua_split_tf32_f32(const float* x, float* hi, float* lo, long long n, void* stream) {
+  using namespace ua;
+  UA_REQUIRE(x && hi && lo && n >= 0, "ua_split_tf32_f32: NULL pointer");
+  UA_REQUIRE(n % 4 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)hi % 16 == 0 && (uintptr_t)lo % 16 == 0,
+             "ua_split_tf32_f32: n must be a multiple of 4 and the pointers 16-byte aligned");
+  if (n == 0) return UA_OK;
+  const long long n4 = n / 4;
+  long long blocks = (n4 + 255) / 256;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  split_tf32_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, hi, lo, n4);
+  return check_launch("ua_split_tf32_f32");
+}
+
+extern "C" int ua_gemm_tf32x3_f32(const float* a_hi, const float* a_lo, long long lda, const float* w_hi,
+                                  const float* w_lo, long long ldw, int M, int N, int K, const float* bias,
+                                  const float* group_bias, int relu, float* out, float* out_hi, float* out_lo,
+                                  long long ldo, float* gmax, float* gmax_hi, float* gmax_lo, void* stream) {
+  using namespace ua;
+  UA_REQUIRE(a_hi && a_lo && w_hi && w_lo, "ua_gemm_tf32x3_f32: NULL operand");
+  UA_REQUIRE(M >= 1 && N >= 1 && K >= 1, "ua_gemm_tf32x3_f32: bad sizes M=%d N=%d K=%d", M, N, K);
+  UA_UNSUPPORTED(N % 128 != 0, "ua_gemm_tf32x3_f32: N=%d must be a multiple of 128", N);
+  UA_UNSUPPORTED(K % kBK != 0, "ua_gemm_tf32x3_f32: K=%d must be a multiple of %d", K, kBK);
+  UA_REQUIRE(lda >= K && ldw >= K && lda % 4 == 0 && ldw % 4 == 0, "ua_gemm_tf32x3_f32: bad leading dimensions");
+  UA_REQUIRE((uintptr_t)a_hi % 16 == 0 && (uintptr_t)a_lo % 16 == 0 && (uintptr_t)w_hi % 16 == 0 &&
+                 (uintptr_t)w_lo % 16 == 0,
+             "ua_gemm_tf32x3_f32: operands must be 16-byte aligned");
+  UA_REQUIRE((out_hi == nullptr) == (out_lo == nullptr), "ua_gemm_tf32x3_f32: out_hi and out_lo come as a pair");
+  UA_REQUIRE((gmax_hi == nullptr) == (gmax_lo == nullptr) && (!gmax_hi || gmax),
+             "ua_gemm_tf32x3_f32: gmax_hi / gmax_lo come as a pair, with gmax");
+  UA_REQUIRE(out || out_hi || gmax, "ua_gemm_tf32x3_f32: no output requested");
+  UA_REQUIRE(!(out || out_hi) || (ldo >= N && ldo % 4 == 0), "ua_gemm_tf32x3_f32: bad ldo");
+  UA_REQUIRE(!gmax || M % 32 == 0, "ua_gemm_tf32x3_f32: the group max needs M %% 32 == 0");
+  GemmParams p;
+  p.M = M, p.N = N, p.K = K, p.bias = bias, p.group_bias = group_bias, p.relu = relu;
+  p.out = out, p.out_hi = out_hi, p.out_lo = out_lo, p.ldo = ldo, p.gmax = gmax, p.gmax_hi = gmax_hi, p.gmax_lo = gmax_lo;
+  const bool wide = N % 256 == 0;
+  const int bn = wide ? 256 : 128;
+  CUtensorMap m_a_hi, m_a_lo, m_w_hi, m_w_lo;
+  int rc;
+  if ((rc = make_map(&m_a_hi, a_hi, M, K, lda, kBM)) != UA_OK) return rc;
+  if ((rc = make_map(&m_a_lo, a_lo, M, K, lda, kBM)) != UA_OK) return rc;
+  if ((rc = make_map(&m_w_hi, w_hi, N, K, ldw, bn)) != UA_OK) return rc;
+  if ((rc = make_map(&m_w_lo, w_lo, N, K, ldw, bn)) != UA_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  return wide ? launch_gemm<256, 2>(m_a_hi, m_a_lo, m_w_hi, m_w_lo, p, st)
+              : launch_gemm<128, 3>(m_a_hi, m_a_lo, m_w_hi, m_w_lo, p, st);
+}
