@@ -33,6 +33,7 @@ N_POINTS, N_CLASSES, FEAT_DIM, MODES = 1024, 40, 512, 8
 # dram__bytes_read.sum + dram__bytes_write.sum of one LVIS-scale launch (ncu --set full, profiles/r1_modedota_lvis.txt):
 # 75.9 MB read + 17.2 MB written inside the kernel; the rest of the 75.8 MB of output is still dirty in L2 at exit.
 LVIS_DRAM_TRAFFIC_BYTES = 93_060_000
+GEMM_DRAM_TRAFFIC_BYTES = None    # filled from the ncu --set full capture of the dominant GEMM launch (profiles/)
 WORKLOAD = "ULIP-2 PointBERT (random init) + MODE-DOTA M=8 + res-learning, synthetic ModelNet40-C streams, 1024 pts, 40 classes, batch 1/stream"
 
 
@@ -42,6 +43,17 @@ def measured_peaks():
         p = json.load(open(path))
         return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measured_tensor_peak():
+    """fp32-equivalent peak of the 3xTF32 tensor-core path: measured dense bf16 TFLOP/s (sustained: the GEMMs run
+    inside a long step) / 2 for tf32 / 3 products per flop."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return float(p.get("bf16_tflops_sustained", p["bf16_tflops"])) / 6.0, \
+            "measured bf16 sustained (MEASURED_PEAKS.json) / 2 (tf32) / 3 (3xTF32)"
+    return 1400.0 / 6.0, "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md) / 2 / 3"
 
 
 class L2Flush:
@@ -229,15 +241,33 @@ def run_ours(args):
         "ua_residual_learn_f32": "one library call = 42 launches (10 Adam steps); fp32 SIMT contraction 40x320x512 per "
                                  "stream, issue-bound, state L2-resident (DESIGN.md)",
     }
-    kern = {n: {"calls_per_step": c // reps, "mean_us": round(m, 2),
-                "achieved_gbs": round(alg_bytes.get(n, 0) / (m * 1e-6) / 1e9, 2)} for n, (c, tot, m) in summ.items()}
+    tensor_peak, tensor_src = measured_tensor_peak()
+    kern = {}
+    for n, (c, tot, m) in summ.items():
+        row = {"calls_per_step": c // reps, "mean_us": round(m, 2), "total_us_per_step": round(tot / reps, 1)}
+        if n in tl.flops:
+            row["achieved_tflops_fp32_equiv"] = round(tl.flops[n] / (tot * 1e-6) / 1e12, 2)
+        else:
+            row["achieved_gbs"] = round(alg_bytes.get(n, 0) / (m * 1e-6) / 1e9, 2)
+        kern[n] = row
     top = max(summ.items(), key=lambda kv: kv[1][1])[0]
-    ach = alg_bytes.get(top, 0) / (summ[top][2] * 1e-6) / 1e9
-    roofline = {"bound": "hbm", "kernel": top, "achieved": round(ach, 3), "peak": peak, "unit": "GB/s",
-                "frac": round(ach / peak, 5), "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes.get(top, 0), "launch_us": round(summ[top][2], 2),
-                "note": notes.get(top, ""),
-                "kernels": kern}
+    if top in tl.flops:
+        # tcgen05 3xTF32 GEMM: fp32-equivalent flops (2MNK per launch, summed over the launches of the step) against
+        # the fp32-equivalent tensor peak = measured bf16 dense peak / 2 (tf32 rate) / 3 (three tf32 products per flop)
+        ach = tl.flops[top] / (summ[top][1] * 1e-6) / 1e12
+        roofline = {"bound": "tensor", "kernel": top + " (gemm_tf32x3_kernel)", "achieved": round(ach, 2),
+                    "peak": round(tensor_peak, 1), "unit": "TFLOP/s", "frac": round(ach / tensor_peak, 4),
+                    "traffic": GEMM_DRAM_TRAFFIC_BYTES, "peak_source": tensor_src,
+                    "algorithmic_flops_per_step": tl.flops[top] // reps, "launches_per_step": summ[top][0] // reps,
+                    "launch_us": round(summ[top][2], 2),
+                    "note": "fp32-equivalent flops; every flop costs three tf32 tensor-core products (3xTF32 split)",
+                    "kernels": kern}
+    else:
+        ach = alg_bytes.get(top, 0) / (summ[top][2] * 1e-6) / 1e9
+        roofline = {"bound": "hbm", "kernel": top, "achieved": round(ach, 3), "peak": peak, "unit": "GB/s",
+                    "frac": round(ach / peak, 5), "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": alg_bytes.get(top, 0), "launch_us": round(summ[top][2], 2),
+                    "note": notes.get(top, ""), "kernels": kern}
     # ---- the HBM-bound kernel of the path at the size where it is HBM-bound (cfg 4: K=1156, M=8, D=1024) ----------
     lv = lvis_cache_roofline(dev, peak, flush)
     roofline["lvis_cache_step"] = lv

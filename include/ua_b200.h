@@ -176,6 +176,9 @@ int ua_align_loss_grad_f32(const float* text0, long long text0_stream_stride, co
  * Limits: N % 128 == 0, K % 32 == 0, 16-byte aligned operands, lda/ldw/ldo multiples of 4.
  * ---------------------------------------------------------------------------------------- */
 int ua_split_tf32_f32(const float* x, float* hi, float* lo, long long n, void* stream);
+/* (hi, lo) of relu?(x[M,C] . w[N,C]^T + b[N]) for the C = 3 / 6 input channels of the group encoder's first conv. */
+int ua_pointwise_linear_split_f32(const float* x, const float* w, const float* b, int relu, long long M, int C, int N,
+                                  float* out_hi, float* out_lo, void* stream);
 int ua_gemm_tf32x3_f32(const float* a_hi, const float* a_lo, long long lda, const float* w_hi, const float* w_lo,
                        long long ldw, int M, int N, int K, const float* bias, const float* group_bias, int relu,
                        float* out, float* out_hi, float* out_lo, long long ldo, float* gmax, float* gmax_hi,

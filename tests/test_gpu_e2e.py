@@ -21,19 +21,22 @@ def make_args(inp, dev):
         text_features=torch.from_numpy(inp["text"]), cpu_rng_parity=True, keep_logits=True)
 
 
-def build(inp, dev):
-    from uniadapter_b200.encoders import UlipPointBert
+def build(inp, dev, tensor_cores=False):
+    from uniadapter_b200.encoders import UlipPointBert, use_tensor_cores
     torch.manual_seed(cases.E2E_MODEL_SEED)
-    return UlipPointBert(depth=inp["depth"]).to(dev).eval()
+    enc = UlipPointBert(depth=inp["depth"]).to(dev).eval()
+    return use_tensor_cores(enc, True) if tensor_cores else enc
 
 
+@pytest.mark.parametrize("tensor_cores", [False, True])
 @pytest.mark.parametrize("name", list(cases.E2E))
-def test_core_loop_vs_reference_loop(name, cuda_device):
-    """Drop-in test_zeroshot_3d_core: per-step predictions bit-exact, logits within the stated fp32 tolerance."""
+def test_core_loop_vs_reference_loop(name, tensor_cores, cuda_device):
+    """Drop-in test_zeroshot_3d_core: per-step predictions bit-exact, logits within the stated fp32 tolerance; with the
+    encoder in plain torch and with its group encoder / Linear layers on the tcgen05 3xTF32 GEMM."""
     from uniadapter_b200.adapter import test_zeroshot_3d_core as core
     inp = cases.e2e_inputs(name)
     gold = load_golden(name, inp)
-    model = build(inp, cuda_device)
+    model = build(inp, cuda_device, tensor_cores)
     pcs = torch.from_numpy(inp["pc"])
     loader = [(pcs[i:i + 1], torch.tensor([0]), ["x"], torch.ones(1, inp["N"], 3)) for i in range(inp["T"])]
     torch.manual_seed(cases.E2E_LOOP_SEED)
@@ -71,8 +74,8 @@ def test_stream_engine_vs_reference_loop(name, cuda_device):
     gold = load_golden(name, inp)
     dev = cuda_device
     S = 3
-    eng = StreamEngine(build(inp, dev), 'ulip', torch.from_numpy(inp["text"]), S, inp["N"], cases.CFG, mode_M=inp["M"],
-                       res_learning=inp["res_learning"], device=dev, use_graph=False)
+    eng = StreamEngine(build(inp, dev, tensor_cores=True), 'ulip', torch.from_numpy(inp["text"]), S, inp["N"], cases.CFG,
+                       mode_M=inp["M"], res_learning=inp["res_learning"], device=dev, use_graph=False)
     pcs = torch.from_numpy(inp["pc"])
     for i, (s0, noise, s1) in enumerate(replay_rng(inp["T"], inp["N"])):
         eng.inject = dict(start=s0.expand(S).contiguous().to(dev), noise=noise.expand(S, -1, -1).contiguous().to(dev),
@@ -93,8 +96,8 @@ def test_stream_engine_cuda_graph(cuda_device):
     inp = cases.e2e_inputs("e2e_ulip_d2_modedota_res")
     dev = cuda_device
     S, T = 4, 6
-    eng = StreamEngine(build(inp, dev), 'ulip', torch.from_numpy(inp["text"]), S, inp["N"], cases.CFG, mode_M=8,
-                       res_learning=True, device=dev, use_graph=True)
+    eng = StreamEngine(build(inp, dev, tensor_cores=True), 'ulip', torch.from_numpy(inp["text"]), S, inp["N"], cases.CFG,
+                       mode_M=8, res_learning=True, device=dev, use_graph=True)
     g = torch.Generator().manual_seed(3)
     for i in range(T):
         final, pred = eng.step(unit_sphere_clouds(S, inp["N"], g).pin_memory())

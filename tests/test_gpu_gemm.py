@@ -1,0 +1,97 @@
+"""GPU: the tcgen05 3xTF32 GEMM, the tensor-core group encoder and Linear plans against plain PyTorch references
+(float64 for the GEMM itself, the fp32 torch modules for the plans)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("shape", [(128, 128, 32), (100, 256, 64), (1000, 384, 384), (2048, 512, 256), (4097, 128, 1536)])
+def test_gemm_tf32x3_vs_float64(shape, cuda_device):
+    """fp32-class accuracy: the error against float64 stays within a small multiple of an fp32 matmul's own error."""
+    from uniadapter_b200.gemm import gemm_tf32x3, split_tf32
+    M, N, K = shape
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(cuda_device)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(cuda_device)
+    b = torch.randn(N, generator=g).to(cuda_device)
+    ap, wp = split_tf32(a), split_tf32(w)
+    assert torch.equal(ap[0] + ap[1], a) and int((ap[0].view(torch.int32) & 0x1fff).abs().max()) == 0
+    out = gemm_tf32x3(ap, wp, bias=b, out=True)['out']
+    ref = a.double() @ w.double().t() + b.double()
+    err = float((out.double() - ref).abs().max())
+    err32 = float(((a @ w.t() + b).double() - ref).abs().max())
+    assert err <= 1e-5 * float(ref.abs().max()) and err <= 12 * err32 + 1e-6, (err, err32)
+
+
+def test_gemm_epilogues(cuda_device):
+    from uniadapter_b200.gemm import gemm_tf32x3, split_tf32
+    M, N, K = 4096, 256, 128
+    g = torch.Generator().manual_seed(1)
+    a = torch.randn(M, K, generator=g).to(cuda_device)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(cuda_device)
+    b = torch.randn(N, generator=g).to(cuda_device)
+    gb = torch.randn(M // 32, N, generator=g).to(cuda_device)
+    res = gemm_tf32x3(split_tf32(a), split_tf32(w), bias=b, group_bias=gb, relu=True, out=True, out_split=True,
+                      group_max_split=True)
+    ref = torch.relu(a.double() @ w.double().t() + b.double() + gb.double().repeat_interleave(32, 0)).float()
+    np.testing.assert_allclose(res['out'].cpu().numpy(), ref.cpu().numpy(), rtol=1e-5, atol=2e-5)
+    hi, lo = res['out_split']
+    assert torch.equal(hi + lo, res['out']) and int((hi.view(torch.int32) & 0x1fff).abs().max()) == 0
+    assert torch.equal(res['gmax'], res['out'].view(M // 32, 32, N).amax(1))
+    gh, gl = res['gmax_split']
+    assert torch.equal(gh + gl, res['gmax'])
+
+
+def test_gemm_rejects_unsupported_shapes(cuda_device):
+    from uniadapter_b200 import _lib
+    from uniadapter_b200.gemm import gemm_tf32x3, split_tf32
+    a = split_tf32(torch.randn(64, 48, device=cuda_device))
+    w = split_tf32(torch.randn(100, 48, device=cuda_device))
+    with pytest.raises(_lib.UaError):
+        gemm_tf32x3(a, w, out=True)
+
+
+@pytest.mark.parametrize("cfg", [(3, 256, 32, 2, 50), (6, 512, 64, 1, 24)])
+def test_group_encoder_plan_vs_torch_module(cfg, cuda_device):
+    """MiniPointNet on the tensor cores (BN folded, concat as per-group bias, fused group max) vs the fp32 torch module
+    evaluated in float64."""
+    from uniadapter_b200.encoders import MiniPointNet
+    from uniadapter_b200.gemm import GroupEncoderPlan
+    C, E, n, bs, g = cfg
+    torch.manual_seed(5)
+    mod = MiniPointNet(C, E).to(cuda_device).eval()
+    with torch.no_grad():
+        for bn in (mod.first_conv[1], mod.second_conv[1]):        # non-trivial running statistics
+            bn.running_mean.normal_(0, 0.1), bn.running_var.uniform_(0.5, 1.5), bn.weight.normal_(1, 0.1), bn.bias.normal_(0, 0.1)
+    x = torch.randn(bs, g, n, C, device=cuda_device) * 0.3
+    plan = GroupEncoderPlan(mod)
+    with torch.no_grad():
+        out = plan(x)
+        ref = mod.double()(x.double()).float()
+    np.testing.assert_allclose(out.cpu().numpy(), ref.cpu().numpy(), rtol=2e-5, atol=2e-5)
+
+
+def test_encoder_with_tensor_cores_matches_torch_encoder(cuda_device):
+    """The whole ULIP encoder with tensor-core plans (group encoder + Linear layers) vs the same encoder in torch fp32
+    with TF32 disabled: features within fp32 round-off, far tighter than the cuDNN TF32 convolutions torch uses."""
+    from uniadapter_b200.encoders import UlipPointBert, use_tensor_cores
+    from uniadapter_b200.streams import unit_sphere_clouds
+    torch.manual_seed(0)
+    enc = UlipPointBert(depth=2).to(cuda_device).eval()
+    pc = unit_sphere_clouds(3, 1024, torch.Generator().manual_seed(2)).to(cuda_device)
+    start = torch.zeros(3, dtype=torch.long, device=cuda_device)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            enc.point_encoder.group_divider.next_start_idx = start
+            ref = enc(pc)
+            use_tensor_cores(enc, True)
+            enc.point_encoder.group_divider.next_start_idx = start
+            out = enc(pc)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    scale = float(ref.abs().max())
+    np.testing.assert_allclose(out.cpu().numpy(), ref.cpu().numpy(), rtol=1e-4, atol=2e-5 * scale)

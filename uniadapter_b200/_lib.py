@@ -43,6 +43,7 @@ SIGNATURES = {
     "ua_align_loss_grad_f32": (_I, [_P, C.c_longlong, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P,
                                      C.c_longlong, _P]),
     "ua_split_tf32_f32": (_I, [_P, _P, _P, C.c_longlong, _P]),
+    "ua_pointwise_linear_split_f32": (_I, [_P, _P, _P, _I, C.c_longlong, _I, _I, _P, _P, _P]),
     "ua_gemm_tf32x3_f32": (_I, [_P, _P, C.c_longlong, _P, _P, C.c_longlong, _I, _I, _I, _P, _P, _I, _P, _P, _P,
                                  C.c_longlong, _P, _P, _P, _P]),
     "ua_dota_fit_f32": (_I, [_P, _P, _I, _P, _P, _P, _P, _I, _I, _P]),
@@ -71,6 +72,7 @@ class _TimedLib:
     def __init__(self, handle):
         self._h = handle
         self.records = {}
+        self.flops = {}
 
     def __getattr__(self, name):
         fn = getattr(self._h, name)
@@ -84,6 +86,8 @@ class _TimedLib:
             rc = fn(*args)
             e.record()
             self.records.setdefault(name, []).append((s, e))
+            if name == "ua_gemm_tf32x3_f32":       # M, N, K -> fp32-equivalent flops of this launch
+                self.flops[name] = self.flops.get(name, 0) + 2 * int(args[6]) * int(args[7]) * int(args[8])
             return rc
 
         return timed

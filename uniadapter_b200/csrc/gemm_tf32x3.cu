@@ -332,6 +332,39 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict
   }
 }
 
+// Point-wise first layer of the group encoder: y = relu?(x . W^T + b) with a tiny inner dimension (C = 3 or 6 input
+// channels), written as the (hi, lo) pair the next GEMM consumes. One thread per (row, 4 output channels).
+template <int C>
+__global__ void __launch_bounds__(256) pointwise_linear_split_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                   const float* __restrict__ b, int relu, long long M,
+                                                                   int N, float* __restrict__ hi, float* __restrict__ lo) {
+  const int n4 = N / 4;
+  const long long total = M * n4;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long row = e / n4;
+    const int c0 = (int)(e - row * n4) * 4;
+    float xin[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) xin[c] = __ldg(x + row * C + c);
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc = fmaf(xin[c], __ldg(w + (size_t)(c0 + j) * C + c), acc);
+      acc += __ldg(b + c0 + j);
+      o[j] = relu ? fmaxf(acc, 0.f) : acc;
+    }
+    float4 h, l;
+    h.x = tf32_round(o[0]), l.x = o[0] - h.x;
+    h.y = tf32_round(o[1]), l.y = o[1] - h.y;
+    h.z = tf32_round(o[2]), l.z = o[2] - h.z;
+    h.w = tf32_round(o[3]), l.w = o[3] - h.w;
+    *reinterpret_cast<float4*>(hi + row * N + c0) = h;
+    *reinterpret_cast<float4*>(lo + row * N + c0) = l;
+  }
+}
+
 // ---- host side -----------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -401,6 +434,24 @@ extern "C" int ua_split_tf32_f32(const float* x, float* hi, float* lo, long long
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
   split_tf32_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, hi, lo, n4);
   return check_launch("ua_split_tf32_f32");
+}
+
+extern "C" int ua_pointwise_linear_split_f32(const float* x, const float* w, const float* b, int relu, long long M, int C,
+                                            int N, float* out_hi, float* out_lo, void* stream) {
+  using namespace ua;
+  UA_REQUIRE(x && w && b && out_hi && out_lo, "ua_pointwise_linear_split_f32: NULL pointer");
+  UA_REQUIRE(M >= 1 && N >= 4 && N % 4 == 0, "ua_pointwise_linear_split_f32: bad sizes M=%lld N=%d", M, N);
+  UA_REQUIRE((uintptr_t)out_hi % 16 == 0 && (uintptr_t)out_lo % 16 == 0, "ua_pointwise_linear_split_f32: unaligned output");
+  UA_UNSUPPORTED(C != 3 && C != 6, "ua_pointwise_linear_split_f32: C=%d input channels (3 or 6 supported)", C);
+  const long long total = M * (N / 4);
+  long long blocks = (total + 255) / 256;
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C == 3)
+    pointwise_linear_split_kernel<3><<<(unsigned)blocks, 256, 0, st>>>(x, w, b, relu, M, N, out_hi, out_lo);
+  else
+    pointwise_linear_split_kernel<6><<<(unsigned)blocks, 256, 0, st>>>(x, w, b, relu, M, N, out_hi, out_lo);
+  return check_launch("ua_pointwise_linear_split_f32");
 }
 
 extern "C" int ua_gemm_tf32x3_f32(const float* a_hi, const float* a_lo, long long lda, const float* w_hi,

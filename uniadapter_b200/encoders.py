@@ -38,11 +38,22 @@ class MiniPointNet(nn.Module):
                                          nn.Conv1d(512, encoder_channel, 1))
 
     def forward(self, point_groups: torch.Tensor) -> torch.Tensor:
+        plan = getattr(self, '_tc_plan', None)
+        if plan is not None and not self.training and point_groups.is_cuda and not torch.is_grad_enabled():
+            return plan(point_groups)                       # tcgen05 path (gemm.GroupEncoderPlan)
         bs, g, n, c = point_groups.shape
         f = self.first_conv(point_groups.reshape(bs * g, n, c).transpose(2, 1))
         f = torch.cat([f.max(dim=2, keepdim=True)[0].expand(-1, -1, n), f], dim=1)
         f = self.second_conv(f).max(dim=2)[0]
         return f.reshape(bs, g, self.encoder_channel)
+
+
+def _linear(mod: nn.Linear, x: torch.Tensor) -> torch.Tensor:
+    """nn.Linear through its tensor-core plan when ``use_tensor_cores`` attached one (inference on CUDA), else torch."""
+    plan = getattr(mod, '_tc_plan', None)
+    if plan is not None and x.is_cuda and not torch.is_grad_enabled():
+        return plan(x)
+    return mod(x)
 
 
 class _Mlp(nn.Module):
@@ -52,7 +63,7 @@ class _Mlp(nn.Module):
         self.fc2 = nn.Linear(hidden, dim)
 
     def forward(self, x):
-        return self.fc2(F.gelu(self.fc1(x)))
+        return _linear(self.fc2, F.gelu(_linear(self.fc1, x)))
 
 
 class _Attention(nn.Module):
@@ -64,9 +75,9 @@ class _Attention(nn.Module):
 
     def forward(self, x):
         B, N, C = x.shape
-        q, k, v = self.qkv(x).reshape(B, N, 3, self.heads, C // self.heads).permute(2, 0, 3, 1, 4)
+        q, k, v = _linear(self.qkv, x).reshape(B, N, 3, self.heads, C // self.heads).permute(2, 0, 3, 1, 4)
         x = F.scaled_dot_product_attention(q, k, v)
-        return self.proj(x.transpose(1, 2).reshape(B, N, C))
+        return _linear(self.proj, x.transpose(1, 2).reshape(B, N, C))
 
 
 class _Block(nn.Module):
@@ -101,7 +112,7 @@ class _PointBertTrunk(nn.Module):
 
     def forward(self, pts):
         neighborhood, center = self.group_divider(pts)
-        tokens = self.reduce_dim(self.encoder(neighborhood))
+        tokens = _linear(self.reduce_dim, self.encoder(neighborhood))
         B = tokens.size(0)
         x = torch.cat((self.cls_token.expand(B, -1, -1), tokens), dim=1)
         pos = torch.cat((self.cls_pos.expand(B, -1, -1), self.pos_embed(center)), dim=1)
@@ -152,7 +163,7 @@ class Uni3DEncoder(nn.Module):
 
     def forward(self, pts, colors):
         _, center, features = self.group_divider(pts, colors)
-        tokens = self.encoder2trans(self.encoder(features))
+        tokens = _linear(self.encoder2trans, self.encoder(features))
         B = tokens.size(0)
         x = torch.cat((self.cls_token.expand(B, -1, -1), tokens), dim=1)
         x = x + torch.cat((self.cls_pos.expand(B, -1, -1), self.pos_embed(center)), dim=1)
@@ -233,9 +244,10 @@ class OpenShapePPAT(nn.Module):
         return self.proj(x[:, 0])
 
 
-def build_encoder(vlm3d: str, seed: int = 0, device='cuda', small: bool = False) -> nn.Module:
+def build_encoder(vlm3d: str, seed: int = 0, device='cuda', small: bool = False, tensor_cores: bool = True) -> nn.Module:
     """Random-init encoder of the named family in eval mode (no checkpoints exist offline).
-    ``small`` shrinks the transformer depth for smoke tests."""
+    ``small`` shrinks the transformer depth for smoke tests. ``tensor_cores`` (CUDA devices) routes the group encoder
+    and the supported Linear layers through the tcgen05 3xTF32 GEMM (``use_tensor_cores``)."""
     torch.manual_seed(seed)
     if vlm3d == 'ulip':
         m = UlipPointBert(depth=2 if small else 12)
@@ -245,7 +257,23 @@ def build_encoder(vlm3d: str, seed: int = 0, device='cuda', small: bool = False)
         m = OpenShapePPAT(depth=2 if small else 12)
     else:
         raise ValueError(f"unknown vlm3d {vlm3d!r}")
-    return m.to(device).float().eval()
+    m = m.to(device).float().eval()
+    if tensor_cores and torch.device(device).type == 'cuda':
+        use_tensor_cores(m, True)
+    return m
+
+
+def use_tensor_cores(model: nn.Module, flag: bool = True, linears: bool = True) -> nn.Module:
+    """Attach (or drop) the tcgen05 3xTF32 plans (gemm.py): the mini-PointNet group encoder and, with ``linears``, the
+    nn.Linear layers whose shapes the GEMM supports (N % 128 == 0, K % 32 == 0). Inference only; weights are folded
+    and split when this is called, so call it again after loading other weights."""
+    from .gemm import GroupEncoderPlan, LinearPlan
+    for mod in model.modules():
+        if isinstance(mod, MiniPointNet):
+            mod._tc_plan = GroupEncoderPlan(mod) if flag else None
+        elif isinstance(mod, nn.Linear) and linears:
+            mod._tc_plan = LinearPlan(mod) if (flag and LinearPlan.supported(mod)) else None
+    return model
 
 
 def set_device_rng(model: nn.Module, flag: bool = True) -> None:

@@ -46,3 +46,90 @@ def gemm_tf32x3(a, w, bias=None, group_bias=None, relu=False, out=False, out_spl
     if group_max_split:
         res['gmax_split'] = (gh, gl)
     return res
+
+
+# ----------------------------------------------------------------------------------------------------------
+# modules built on the GEMM: the group encoder (mini-PointNet) and nn.Linear
+# ----------------------------------------------------------------------------------------------------------
+def _fold_bn(conv_w, conv_b, bn):
+    """Conv1d(k=1) followed by BatchNorm1d in eval mode -> one affine map (W', b')."""
+    s = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+    w = conv_w.squeeze(-1) * s[:, None]
+    b = (conv_b - bn.running_mean) * s + bn.bias
+    return w.contiguous(), b.contiguous()
+
+
+class GroupEncoderPlan:
+    """Inference plan of a ``MiniPointNet`` (eval mode) on the tensor-core GEMM (models/ulip/pointbert/dvae.py:201-215,
+    models/point_encoder.py:145-159):
+
+        h1 = relu(bn(conv1(x)))                 point-wise kernel (C = 3 / 6 input channels) -> (hi, lo)
+        f  = conv2(h1);  g = max_points(f)      GEMM K=128, epilogue: (hi, lo) store + max over the 32-row groups
+        h3 = relu(bn(conv3([g, f])))            = relu(f . W3f'^T + (g . W3g'^T + b3'))  — the concatenation with the
+                                                broadcast global feature becomes a per-group bias (one small GEMM)
+        out = max_points(conv4(h3))             GEMM K=512, epilogue: max over the 32-row groups only (conv4's output
+                                                is never written)
+    BatchNorm is folded into the convolutions; weights are split into (hi, lo) once."""
+
+    def __init__(self, module):
+        with torch.no_grad():
+            c1, bn1, _, c2 = module.first_conv
+            c3, bn3, _, c4 = module.second_conv
+            self.C = c1.in_channels
+            self.E = c4.out_channels
+            self.w1, self.b1 = _fold_bn(c1.weight, c1.bias, bn1)                      # (128, C)
+            self.w2 = split_tf32(c2.weight.squeeze(-1))                               # (256, 128)
+            self.b2 = c2.bias.detach().clone().contiguous()
+            w3, self.b3 = _fold_bn(c3.weight, c3.bias, bn3)                           # (512, 512): [global | local]
+            self.w3g = split_tf32(w3[:, :256])
+            self.w3f = split_tf32(w3[:, 256:])
+            self.w4 = split_tf32(c4.weight.squeeze(-1))                               # (E, 512)
+            self.b4 = c4.bias.detach().clone().contiguous()
+
+    @torch.no_grad()
+    def __call__(self, point_groups: torch.Tensor) -> torch.Tensor:
+        bs, g, n, c = point_groups.shape
+        if n % 32 or c != self.C:
+            raise _lib.UaError(f"group encoder: group size {n} must be a multiple of 32 and channels {c} == {self.C}")
+        M, r = bs * g * n, n // 32
+        x = point_groups.reshape(M, c).contiguous()
+        dev = x.device
+        h1 = (torch.empty((M, 128), device=dev), torch.empty((M, 128), device=dev))
+        rc = _lib.lib().ua_pointwise_linear_split_f32(_lib.ptr(x), _lib.ptr(self.w1), _lib.ptr(self.b1), 1, M, c, 128,
+                                                       _lib.ptr(h1[0]), _lib.ptr(h1[1]), _lib.stream_ptr())
+        _lib.check(rc, "ua_pointwise_linear_split_f32")
+        res = gemm_tf32x3(h1, self.w2, bias=self.b2, out_split=True, group_max=(r > 1), group_max_split=(r == 1))
+        f = res['out_split']
+        if r == 1:
+            gpair = res['gmax_split']
+        else:            # groups of 64 points span two 32-row halves
+            gpair = split_tf32(res['gmax'].view(-1, r, 256).amax(1))
+        gbias = gemm_tf32x3(gpair, self.w3g, bias=self.b3, out=True)['out']                  # (bs*g, 512)
+        if r > 1:
+            gbias = gbias.repeat_interleave(r, 0).contiguous()
+        h3 = gemm_tf32x3(f, self.w3f, group_bias=gbias, relu=True, out_split=True)['out_split']
+        out = gemm_tf32x3(h3, self.w4, bias=self.b4, group_max=True)['gmax']                 # (M/32, E)
+        if r > 1:
+            out = out.view(-1, r, self.E).amax(1)
+        return out.reshape(bs, g, self.E)
+
+
+class LinearPlan:
+    """nn.Linear on the tensor-core GEMM: y = x @ W^T + b with W split once; x is split per call."""
+
+    def __init__(self, linear):
+        with torch.no_grad():
+            self.w = split_tf32(linear.weight)
+            self.b = linear.bias.detach().clone().contiguous() if linear.bias is not None else None
+            self.N, self.K = linear.weight.shape
+
+    @staticmethod
+    def supported(linear) -> bool:
+        n, k = linear.weight.shape
+        return n % 128 == 0 and k % 32 == 0
+
+    @torch.no_grad()
+    def __call__(self, x: torch.Tensor, relu=False) -> torch.Tensor:
+        lead = x.shape[:-1]
+        a = split_tf32(x.reshape(-1, self.K))
+        return gemm_tf32x3(a, self.w, bias=self.b, relu=relu, out=True)['out'].reshape(*lead, self.N)
