@@ -34,7 +34,9 @@ const char* ua_last_error(void);
 /* Number of kernel launches issued by this library since load (or since ua_reset_launch_count). */
 int64_t ua_launch_count(void);
 void ua_reset_launch_count(void);
-/* Tuning knobs for experiments: "fps_threads", "knn_warps", "modedota_threads" (0 = built-in heuristic). */
+/* Tuning knobs for experiments (0 = built-in heuristic): "fps_threads", "knn_warps", "modedota_threads",
+ * "modedota_v" (float4 per lane of the single-sample cache kernel; -1 disables that kernel), "modedota_groups",
+ * "modedota_logprod" (1 = product-form log-determinant, the default; 0 = one logf per element). */
 int ua_set_tuning(const char* key, int value);
 
 /* ------------------------------------------------------------------------------------------

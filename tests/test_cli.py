@@ -1,0 +1,37 @@
+"""The drop-in process entry ``main_test-time.py``: the reference's flags (utils/params.py:23,87-111) on the B200 path."""
+import importlib.util
+import os
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def load_main():
+    spec = importlib.util.spec_from_file_location("main_test_time", os.path.join(ROOT, "main_test-time.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_flags_follow_the_reference_and_fix_d1():
+    m = load_main()
+    a = m.parse_args([])                                   # reference defaults: MODE-DOTA (M=4) + residual learning
+    assert a.use_mode_dota and a.res_learning and not a.use_dota and a.mode_M == 4 and a.vlm3d == 'uni3d'
+    assert (a.dota_epsilon, a.dota_sigma, a.dota_eta, a.dota_rho) == (1e-4, 1e-4, 0.1, 0.02)
+    assert a.batch_size == 1 and a.npoints == 1024 and a.seed == 42 and a.device == 'cuda:0'
+    a = m.parse_args(['--use-dota'])                       # reachable here: selects the DOTA branch
+    assert a.use_dota and not a.use_mode_dota and not a.res_learning
+    a = m.parse_args(['--vlm3d', 'ulip', '--mode-M', '8', '--no-res-learning'])
+    assert a.use_mode_dota and not a.res_learning and a.mode_M == 8
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flags", [['--mode-M', '8'], ['--use-dota'], ['--mode-M', '4', '--no-res-learning']])
+def test_cli_runs_a_stream_on_the_gpu(flags, cuda_device, tmp_path):
+    m = load_main()
+    out = m.main(['--vlm3d', 'ulip', '--small-encoder', '--corruption', 'gaussian', '--stream-length', '5',
+                  '--num-classes', '12', '--output-dir', str(tmp_path)] + flags)
+    (res,) = out.values()
+    assert 0.0 <= res['acc1'] <= 100.0 and len(res['times_ms']) == 5
+    assert res['preds'].shape == (5,) and int(res['preds'].max()) < 12

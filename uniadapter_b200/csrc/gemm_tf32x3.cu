@@ -147,7 +147,8 @@ struct SmemLayout {
   static constexpr int kABytes = kBM * kBK * 4;       // 16 KB
   static constexpr int kBBytes = BN * kBK * 4;
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
-  static constexpr int kTotal = STAGES * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
+  static constexpr int kBiasBytes = 4 * BN * 4;       // one effective bias row per epilogue warp
+  static constexpr int kTotal = STAGES * kStageBytes + kBiasBytes + 1024 /* alignment slack */ + 256 /* barriers */;
 };
 
 template <int BN, int STAGES>
@@ -159,7 +160,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   extern __shared__ unsigned char s_raw[];
   // 128B-swizzled tiles need 1024-byte alignment
   unsigned char* s_tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(s_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* s_full = reinterpret_cast<uint64_t*>(s_tiles + STAGES * L::kStageBytes);   // [STAGES]
+  float* s_bias = reinterpret_cast<float*>(s_tiles + STAGES * L::kStageBytes);           // [4 warps][BN]
+  uint64_t* s_full = reinterpret_cast<uint64_t*>(s_tiles + STAGES * L::kStageBytes + L::kBiasBytes);   // [STAGES]
   uint64_t* s_empty = s_full + STAGES;                                                   // [STAGES]
   uint64_t* s_tfull = s_empty + STAGES;                                                  // [2]
   uint64_t* s_tempty = s_tfull + 2;                                                      // [2]
@@ -243,6 +245,23 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       const int row = m_idx + quarter * 32 + lane;
       const bool row_ok = row < p.M;
       const int group = (m_idx + quarter * 32) >> 5;       // 32-row group of this warp
+      // effective bias row of this warp (bias[N] + group_bias[group, N]) into shared memory while the MMAs of the
+      // tile are still running: the chunk loop below then reads it with broadcast loads instead of stalling on HBM
+      const bool has_bias = p.bias != nullptr || p.group_bias != nullptr;
+      float* my_bias = s_bias + (warp - 2) * BN;
+      if (has_bias) {
+        const bool grp_ok = p.group_bias != nullptr && m_idx + quarter * 32 < p.M;
+#pragma unroll
+        for (int c = lane * 4; c < BN; c += 128) {
+          float4 b = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n_idx + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (grp_ok) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(p.group_bias + (size_t)group * p.N + n_idx + c));
+            b.x += g.x, b.y += g.y, b.z += g.z, b.w += g.w;
+          }
+          *reinterpret_cast<float4*>(my_bias + c) = b;
+        }
+        __syncwarp();
+      }
       mbar_wait(&s_tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
@@ -251,18 +270,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         float v[32];
         tmem_ld_32x32(t_row + (uint32_t)c0, v);
         const int col = n_idx + c0;
-        if (p.bias) {
+        if (has_bias) {
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col + i));
-            v[i] += b.x, v[i + 1] += b.y, v[i + 2] += b.z, v[i + 3] += b.w;
-          }
-        }
-        if (p.group_bias) {
-          const float* gb = p.group_bias + (size_t)group * p.N + col;
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(gb + i));
+            const float4 b = *reinterpret_cast<const float4*>(my_bias + c0 + i);
             v[i] += b.x, v[i + 1] += b.y, v[i + 2] += b.z, v[i + 3] += b.w;
           }
         }
@@ -307,7 +318,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         }
       }
       tc_fence_before();
-      __syncwarp();
+      __syncwarp();                                        // also orders this tile's bias reads before the next staging
       if (lane == 0) mbar_arrive(&s_tempty[acc]);
       if (++acc == 2) acc = 0, acc_phase ^= 1u;
     }
