@@ -75,8 +75,9 @@ def test_residual_learner_vs_torch_autograd_adam(shape, cuda_device):
     assert int(learner.adam_t[0]) == 20
 
     class View:       # the reference-shaped model object compute_text_alignment_loss expects
-        def __init__(self, s):
-            self.mu, self.var, self.pi, self.eps = cache.mu[s], cache.var[s], cache.pi[s], cache.epsilon
+        def __init__(self, s, dtype):
+            self.mu, self.var, self.pi = cache.mu[s].to(dtype), cache.var[s].to(dtype), cache.pi[s].to(dtype)
+            self.eps = cache.epsilon
 
         def _get_var(self):
             return torch.clamp(self.var + self.eps, min=1e-8)
@@ -85,30 +86,38 @@ def test_residual_learner_vs_torch_autograd_adam(shape, cuda_device):
             diff = x.unsqueeze(1).unsqueeze(2) - mu.unsqueeze(0)
             return -0.5 * (torch.sum(torch.log(var.unsqueeze(0)), dim=-1) + torch.sum(diff ** 2 / var.unsqueeze(0), dim=-1))
 
-    for s in range(S):
-        res = torch.zeros(K, D, device=dev, requires_grad=True)
+    def torch_loop(s, dtype):
+        t0 = text.to(dtype)
+        res = torch.zeros(K, D, device=dev, dtype=dtype, requires_grad=True)
         opt = torch.optim.Adam([res], lr=1e-3)
-        ref_losses = []
+        ls = []
         for _ in range(20):
-            emb = text + res
+            emb = t0 + res
             emb = emb / emb.norm(dim=1, keepdim=True)
-            loss, _ = compute_text_alignment_loss(emb, View(s))
-            ref_losses.append(float(loss.detach()))
+            loss, _ = compute_text_alignment_loss(emb, View(s, dtype))
+            ls.append(float(loss.detach()))
             opt.zero_grad()
             loss.backward()
             opt.step()
-        ref_text = torch.nn.functional.normalize(text + res.detach(), dim=1)
-        np.testing.assert_allclose(losses[s].cpu().numpy(), np.array(ref_losses[10:]), rtol=3e-4)   # 11th..20th step
-        # Adam normalises every element's step to ~lr: elements whose gradient is numerically zero are
-        # ill-conditioned, so the residuals are compared in aggregate and the text rows (what the head sees) tightly
-        d = (learner.residual[s] - res.detach()).abs()
-        dt = (learner.text[s] - ref_text).abs()
-        cos = (learner.text[s] * ref_text).sum(-1)
-        stats = dict(res_mean=float(d.mean()), res_frac_gt_1e3=float((d > 1e-3).float().mean()), res_max=float(d.max()),
-                     text_max=float(dt.max()), text_frac_gt_2e4=float((dt > 2e-4).float().mean()), cos_min=float(cos.min()),
-                     moved=float(res.detach().abs().mean()))
-        assert stats["res_mean"] < 0.02 * stats["moved"] and stats["res_frac_gt_1e3"] < 1e-2, stats
-        assert stats["text_max"] < 2e-2 and stats["text_frac_gt_2e4"] < 2e-2 and stats["cos_min"] > 1 - 1e-5, stats
+        return res.detach(), torch.nn.functional.normalize(t0 + res.detach(), dim=1), np.array(ls)
+
+    # Adam moves every element by ~lr per step whatever the size of its gradient, so elements whose gradient is
+    # numerically zero follow rounding noise: the yardstick is the distance of torch's OWN fp32 run from a float64 run
+    # of the same loop. The CUDA path must be as close to float64 as torch fp32 is (x3), and the text rows the head sees
+    # must agree to 1e-5 in cosine.
+    for s in range(S):
+        r64, t64, l64 = torch_loop(s, torch.float64)
+        r32, t32, l32 = torch_loop(s, torch.float32)
+        d_ref = (r32.double() - r64).abs()
+        d_our = (learner.residual[s].double() - r64).abs()
+        stats = dict(ours_mean=float(d_our.mean()), torch32_mean=float(d_ref.mean()), ours_max=float(d_our.max()),
+                     torch32_max=float(d_ref.max()), moved=float(r64.abs().mean()))
+        assert stats["ours_mean"] <= 3.0 * stats["torch32_mean"] + 1e-7, stats
+        assert stats["ours_max"] <= 3.0 * stats["torch32_max"] + 1e-3, stats
+        loss_err = np.abs(losses[s].cpu().numpy() - l64[10:]).max()
+        assert loss_err <= 3.0 * np.abs(l32[10:] - l64[10:]).max() + 1e-5, (loss_err, np.abs(l32 - l64).max())
+        cos = (learner.text[s].double() * t64).sum(-1)
+        assert float(cos.min()) > 1 - 1e-5, float(cos.min())
 
 
 def test_residual_learner_refresh_only(cuda_device):
