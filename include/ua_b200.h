@@ -107,6 +107,13 @@ int ua_gather_points_f32(const float* in, const int32_t* idx, int B, int C, int 
  * ---------------------------------------------------------------------------------------- */
 int ua_head_f32(const float* x, int B, int D, const float* text, int num_text, int K, float scale, float* out_xnorm,
                 float* out_logits, float* out_prob, float* out_entropy, int32_t* out_argmax, void* stream);
+/* Batched head on the tensor cores (B >= 64): ua_head_prepare_f32 writes xnorm and the (hi, lo) pair of scale*xnorm,
+ * ua_gemm_tf32x3_f32 contracts it with the (hi, lo) text rows (K padded to a multiple of 128 with zero rows, ld = Kpad),
+ * ua_row_stats_f32 finishes softmax / entropy / first-index argmax over the first K columns of each row. */
+int ua_head_prepare_f32(const float* x, int B, int D, float scale, float* out_xnorm, float* out_hi, float* out_lo,
+                        void* stream);
+int ua_row_stats_f32(const float* logits, int B, int K, long long ld, float* out_prob, float* out_entropy,
+                     int32_t* out_argmax, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * MODE-DOTA (diagonal Gaussian mixture cache)
@@ -172,7 +179,8 @@ int ua_align_loss_grad_f32(const float* text0, long long text0_stream_stride, co
  * Replaces: the zero-shot head contraction at batch >= 64 (Uni_Adapter.py:61-62), the mini-PointNet group encoder's
  * 1x1 convolutions (models/ulip/pointbert/dvae.py:201-215, models/point_encoder.py:145-159).
  * Operands come as (hi, lo) pairs: hi = tf32(x), lo = x - hi (ua_split_tf32_f32, or the OUT_SPLIT epilogue of the
- * producing GEMM). Epilogue: + bias[N], + group_bias[row/32, N], ReLU, then any of
+ * producing GEMM). Epilogue: + bias[N], + group_bias[row/32, N], + residual[M,ldo], act (0 none, 1 ReLU, 2 erf-GELU),
+ * then any of
  *   out [M,ldo] fp32;  (out_hi, out_lo) [M,ldo];  gmax [M/32, N] = max over each 32 consecutive rows (one point
  *   group; needs M % 32 == 0) with an optional (gmax_hi, gmax_lo) copy.
  * Limits: N % 128 == 0, K % 32 == 0, 16-byte aligned operands, lda/ldw/ldo multiples of 4.
@@ -182,9 +190,13 @@ int ua_split_tf32_f32(const float* x, float* hi, float* lo, long long n, void* s
 int ua_pointwise_linear_split_f32(const float* x, const float* w, const float* b, int relu, long long M, int C, int N,
                                   float* out_hi, float* out_lo, void* stream);
 int ua_gemm_tf32x3_f32(const float* a_hi, const float* a_lo, long long lda, const float* w_hi, const float* w_lo,
-                       long long ldw, int M, int N, int K, const float* bias, const float* group_bias, int relu,
-                       float* out, float* out_hi, float* out_lo, long long ldo, float* gmax, float* gmax_hi,
-                       float* gmax_lo, void* stream);
+                       long long ldw, int M, int N, int K, const float* bias, const float* group_bias,
+                       const float* residual, int act, float* out, float* out_hi, float* out_lo, long long ldo,
+                       float* gmax, float* gmax_hi, float* gmax_lo, void* stream);
+/* (hi, lo) of LayerNorm(x (+ pos)) over the last dimension C (C % 128 == 0, C <= 1024); out_sum = x + pos (optional):
+ * the operand producer in front of a transformer block's GEMMs (one warp per row). */
+int ua_layernorm_split_f32(const float* x, const float* pos, const float* gamma, const float* beta, float eps,
+                           long long rows, int C, float* out_sum, float* out_hi, float* out_lo, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * DOTA (full covariance)

@@ -35,3 +35,17 @@ def test_cli_runs_a_stream_on_the_gpu(flags, cuda_device, tmp_path):
     (res,) = out.values()
     assert 0.0 <= res['acc1'] <= 100.0 and len(res['times_ms']) == 5
     assert res['preds'].shape == (5,) and int(res['preds'].max()) < 12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("family", [('uni3d', 2048, 24), ('openshape', 2048, 15)])
+def test_cli_other_encoder_families(family, cuda_device, tmp_path):
+    """Uni3D (FPS start 0, 64-point groups with colour, cfg 4 / 5 geometry) and OpenShape (ball query, cfg 3 geometry)
+    through the same drop-in loop with MODE-DOTA M=8."""
+    vlm3d, npoints, classes = family
+    m = load_main()
+    out = m.main(['--vlm3d', vlm3d, '--small-encoder', '--corruption', 'shear', '--stream-length', '3', '--npoints',
+                  str(npoints), '--num-classes', str(classes), '--mode-M', '8', '--no-res-learning', '--output-dir',
+                  str(tmp_path)])
+    (res,) = out.values()
+    assert len(res['times_ms']) == 3 and int(res['preds'].max()) < classes

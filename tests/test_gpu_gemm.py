@@ -95,3 +95,78 @@ def test_encoder_with_tensor_cores_matches_torch_encoder(cuda_device):
         torch.backends.cudnn.allow_tf32 = old
     scale = float(ref.abs().max())
     np.testing.assert_allclose(out.cpu().numpy(), ref.cpu().numpy(), rtol=1e-4, atol=2e-5 * scale)
+
+
+def test_layernorm_split_and_fused_epilogues(cuda_device):
+    """(x + pos) -> LayerNorm -> (hi, lo); GELU / residual epilogues of the GEMM; against torch in float64."""
+    from uniadapter_b200.gemm import gemm_tf32x3, layernorm_split, split_tf32
+    dev = cuda_device
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(5, 77, 384, generator=g).to(dev)
+    pos = torch.randn(5, 77, 384, generator=g).to(dev)
+    ln = torch.nn.LayerNorm(384).to(dev)
+    with torch.no_grad():
+        ln.weight.normal_(1, 0.2), ln.bias.normal_(0, 0.2)
+        (hi, lo), s = layernorm_split(x, ln, pos, want_sum=True)
+        ref = ln.double()((x + pos).double()).float()
+    assert torch.equal(s, x + pos)
+    np.testing.assert_allclose((hi + lo).cpu().numpy(), ref.cpu().numpy(), rtol=1e-5, atol=1e-5)
+    assert int((hi.view(torch.int32) & 0x1fff).abs().max()) == 0
+    M, N, K = 385, 256, 384
+    a = (hi + lo).view(M, K)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev)
+    b = torch.randn(N, generator=g).to(dev)
+    r = torch.randn(M, N, generator=g).to(dev)
+    pre = a.double() @ w.double().t() + b.double()
+    out = gemm_tf32x3((hi.view(M, K), lo.view(M, K)), split_tf32(w), bias=b, act='gelu', out=True, out_split=True)
+    np.testing.assert_allclose(out['out'].cpu().numpy(), torch.nn.functional.gelu(pre).float().cpu().numpy(), rtol=1e-5, atol=5e-5)
+    assert torch.equal(out['out_split'][0] + out['out_split'][1], out['out'])
+    out = gemm_tf32x3((hi.view(M, K), lo.view(M, K)), split_tf32(w), bias=b, residual=r, out=True)['out']
+    np.testing.assert_allclose(out.cpu().numpy(), (pre + r.double()).float().cpu().numpy(), rtol=1e-5, atol=5e-5)
+
+
+def test_block_plan_vs_torch_block(cuda_device):
+    from uniadapter_b200.encoders import _Block
+    from uniadapter_b200.gemm import BlockPlan
+    dev = cuda_device
+    torch.manual_seed(4)
+    blk = _Block(384, 6).to(dev).eval()
+    x = torch.randn(3, 513, 384, device=dev)
+    pos = torch.randn(3, 513, 384, device=dev) * 0.1
+    with torch.no_grad():
+        out = BlockPlan(blk)(x, pos)
+        ref = blk.double()(x.double(), pos.double()).float()
+    np.testing.assert_allclose(out.cpu().numpy(), ref.cpu().numpy(), rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("shape", [(64, 1024, 55), (64, 1024, 1156), (200, 512, 216)])
+def test_tensor_core_head_vs_simt_head_and_golden(shape, cuda_device):
+    """Batched zero-shot head on the tcgen05 GEMM (cfg 5 shapes) against the SIMT head kernel; the golden b64 case too."""
+    import uniadapter_b200 as ua
+    from uniadapter_b200.head import HeadPlan
+    from oracle import synth
+    B, D, K = shape
+    text = torch.from_numpy(synth.unit_rows(K, D, 9)).to(cuda_device)
+    x = torch.randn(B, D, generator=torch.Generator().manual_seed(B)).to(cuda_device)
+    xn, logits, ent, prob, arg = HeadPlan(text)(x)
+    xn0, logits0, ent0, prob0, arg0 = ua.zero_shot_head(x, text)
+    assert torch.equal(xn, xn0)
+    np.testing.assert_allclose(logits.cpu().numpy(), logits0.cpu().numpy(), rtol=1e-4, atol=5e-5)
+    np.testing.assert_allclose(prob.cpu().numpy(), prob0.cpu().numpy(), rtol=2e-4, atol=1e-7)
+    np.testing.assert_allclose(ent.cpu().numpy(), ent0.cpu().numpy(), rtol=2e-4, atol=1e-6)
+    assert torch.equal(arg, arg0)
+
+
+def test_tensor_core_head_vs_reference_golden(cuda_device):
+    from conftest import load_golden
+    from oracle import cases
+    from uniadapter_b200.head import HeadPlan
+    name = "head_b64_d1024_k55"
+    inp = cases.head_inputs(name)
+    gold = load_golden(name, inp)
+    dev = cuda_device
+    xn, logits, ent, prob, arg = HeadPlan(torch.from_numpy(inp["text"]).to(dev))(torch.from_numpy(inp["x"]).to(dev))
+    np.testing.assert_allclose(xn.cpu().numpy(), gold["xnorm"], rtol=1e-5, atol=1e-8)
+    np.testing.assert_allclose(logits.cpu().numpy(), gold["logits"], rtol=1e-4, atol=5e-5)
+    np.testing.assert_allclose(prob.cpu().numpy(), gold["prob"], rtol=2e-4, atol=1e-7)
+    np.testing.assert_array_equal(arg.cpu().numpy(), gold["pred"])

@@ -35,6 +35,8 @@ SIGNATURES = {
     "ua_ball_group_f32": (_I, [_P, _P, _I, _P, _I, _I, _I, _F, _I, _P, _I, _P, _P]),
     "ua_gather_points_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
     "ua_head_f32": (_I, [_P, _I, _I, _P, _I, _I, _F, _P, _P, _P, _P, _P, _P]),
+    "ua_head_prepare_f32": (_I, [_P, _I, _I, _F, _P, _P, _P, _P]),
+    "ua_row_stats_f32": (_I, [_P, _I, _I, C.c_longlong, _P, _P, _P, _P]),
     "ua_modedota_step_f32": (_I, [_P, _I, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _I, _I, _P]),
     "ua_fuse_logits_f32": (_I, [_P, _P, _I, _I, _I, _P, _I, _I, _F, _F, _F, _F, _F, _I, _P, _P, _P, _P]),
     "ua_residual_scratch_floats": (C.c_longlong, [_I, _I, _I, _I]),
@@ -44,8 +46,9 @@ SIGNATURES = {
                                      C.c_longlong, _P]),
     "ua_split_tf32_f32": (_I, [_P, _P, _P, C.c_longlong, _P]),
     "ua_pointwise_linear_split_f32": (_I, [_P, _P, _P, _I, C.c_longlong, _I, _I, _P, _P, _P]),
-    "ua_gemm_tf32x3_f32": (_I, [_P, _P, C.c_longlong, _P, _P, C.c_longlong, _I, _I, _I, _P, _P, _I, _P, _P, _P,
+    "ua_gemm_tf32x3_f32": (_I, [_P, _P, C.c_longlong, _P, _P, C.c_longlong, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P,
                                  C.c_longlong, _P, _P, _P, _P]),
+    "ua_layernorm_split_f32": (_I, [_P, _P, _P, _P, _F, C.c_longlong, _I, _P, _P, _P, _P]),
     "ua_dota_fit_f32": (_I, [_P, _P, _I, _P, _P, _P, _P, _I, _I, _P]),
     "ua_dota_predict_f16": (_I, [_P, _I, _P, _P, _I, _I, _P, _P]),
     "ua_dota_regularize_f32": (_I, [_P, _I, _F, _P, _P]),

@@ -32,7 +32,8 @@ struct GemmParams {
   int M, N, K;
   const float* bias;        // [N] or null
   const float* group_bias;  // [ceil(M/32), N] or null: added to every row of a 32-row group
-  int relu;
+  int act;                  // 0 none, 1 ReLU, 2 GELU (erf form, torch.nn.functional.gelu default)
+  const float* residual;    // [M, ldo] or null: added after the bias (transformer skip connection)
   float* out;               // [M, ldo] fp32 or null
   float* out_hi;            // [M, ldo] or null (with out_lo)
   float* out_lo;
@@ -277,9 +278,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
             v[i] += b.x, v[i + 1] += b.y, v[i + 2] += b.z, v[i + 3] += b.w;
           }
         }
-        if (p.relu) {
+        if (p.residual && row_ok) {
+          const float4* rp = reinterpret_cast<const float4*>(p.residual + (size_t)row * p.ldo + col);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 r4 = __ldg(rp + i);
+            v[4 * i] += r4.x, v[4 * i + 1] += r4.y, v[4 * i + 2] += r4.z, v[4 * i + 3] += r4.w;
+          }
+        }
+        if (p.act == 1) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+        } else if (p.act == 2) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0.5f * v[i] * (1.0f + erff(v[i] * 0.70710678118654752f));
         }
         if (p.out && row_ok) {
           float4* o = reinterpret_cast<float4*>(p.out + (size_t)row * p.ldo + col);
@@ -376,6 +388,63 @@ __global__ void __launch_bounds__(256) pointwise_linear_split_kernel(const float
   }
 }
 
+// LayerNorm over the last dimension fused with the optional position-embedding add in front of it and the (hi, lo)
+// split behind it: s = x (+ pos); y = (s - mean) * rsqrt(var + eps) * gamma + beta. One warp per row, the row in
+// registers (C <= 32 * 4 * kLnVec), two-pass variance. out_sum (the skip-connection input) is optional.
+constexpr int kLnVec = 8;   // float4 per lane: rows up to 1024 floats
+__global__ void __launch_bounds__(256) layernorm_split_kernel(const float* __restrict__ x, const float* __restrict__ pos,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              float eps, long long rows, int C, float* __restrict__ out_sum,
+                                                              float* __restrict__ out_hi, float* __restrict__ out_lo) {
+  const int lane = threadIdx.x & 31;
+  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nvec = C / 128;           // float4 per lane (C % 128 == 0)
+  float4 v[kLnVec];
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < kLnVec; ++j) {
+    if (j < nvec) {
+      const size_t o = (size_t)row * C + j * 128 + lane * 4;
+      v[j] = __ldg(reinterpret_cast<const float4*>(x + o));
+      if (pos) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(pos + o));
+        v[j].x += q.x, v[j].y += q.y, v[j].z += q.z, v[j].w += q.w;
+      }
+      if (out_sum) *reinterpret_cast<float4*>(out_sum + o) = v[j];
+      sum += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    }
+  }
+  const float mean = warp_sum(sum) / (float)C;
+  float sq = 0.f;
+#pragma unroll
+  for (int j = 0; j < kLnVec; ++j) {
+    if (j < nvec) {
+      const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+      sq += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
+#pragma unroll
+  for (int j = 0; j < kLnVec; ++j) {
+    if (j < nvec) {
+      const int c0 = j * 128 + lane * 4;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c0));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c0));
+      float y[4] = {(v[j].x - mean) * rstd * g.x + b.x, (v[j].y - mean) * rstd * g.y + b.y,
+                    (v[j].z - mean) * rstd * g.z + b.z, (v[j].w - mean) * rstd * g.w + b.w};
+      float4 h, l;
+      h.x = tf32_round(y[0]), l.x = y[0] - h.x;
+      h.y = tf32_round(y[1]), l.y = y[1] - h.y;
+      h.z = tf32_round(y[2]), l.z = y[2] - h.z;
+      h.w = tf32_round(y[3]), l.w = y[3] - h.w;
+      const size_t o = (size_t)row * C + c0;
+      *reinterpret_cast<float4*>(out_hi + o) = h;
+      *reinterpret_cast<float4*>(out_lo + o) = l;
+    }
+  }
+}
+
 // ---- host side -----------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -447,6 +516,22 @@ extern "C" int ua_split_tf32_f32(const float* x, float* hi, float* lo, long long
   return check_launch("ua_split_tf32_f32");
 }
 
+extern "C" int ua_layernorm_split_f32(const float* x, const float* pos, const float* gamma, const float* beta, float eps,
+                                     long long rows, int C, float* out_sum, float* out_hi, float* out_lo, void* stream) {
+  using namespace ua;
+  UA_REQUIRE(x && gamma && beta && out_hi && out_lo && rows >= 1, "ua_layernorm_split_f32: NULL pointer / no rows");
+  UA_UNSUPPORTED(C % 128 != 0 || C > 128 * kLnVec, "ua_layernorm_split_f32: C=%d must be a multiple of 128, <= %d", C,
+                 128 * kLnVec);
+  UA_REQUIRE((uintptr_t)x % 16 == 0 && (uintptr_t)out_hi % 16 == 0 && (uintptr_t)out_lo % 16 == 0 &&
+                 (uintptr_t)gamma % 16 == 0 && (uintptr_t)beta % 16 == 0 && (!pos || (uintptr_t)pos % 16 == 0) &&
+                 (!out_sum || (uintptr_t)out_sum % 16 == 0),
+             "ua_layernorm_split_f32: pointers must be 16-byte aligned");
+  const long long blocks = (rows + 7) / 8;
+  layernorm_split_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, pos, gamma, beta, eps, rows, C, out_sum,
+                                                                           out_hi, out_lo);
+  return check_launch("ua_layernorm_split_f32");
+}
+
 extern "C" int ua_pointwise_linear_split_f32(const float* x, const float* w, const float* b, int relu, long long M, int C,
                                             int N, float* out_hi, float* out_lo, void* stream) {
   using namespace ua;
@@ -467,8 +552,9 @@ extern "C" int ua_pointwise_linear_split_f32(const float* x, const float* w, con
 
 extern "C" int ua_gemm_tf32x3_f32(const float* a_hi, const float* a_lo, long long lda, const float* w_hi,
                                   const float* w_lo, long long ldw, int M, int N, int K, const float* bias,
-                                  const float* group_bias, int relu, float* out, float* out_hi, float* out_lo,
-                                  long long ldo, float* gmax, float* gmax_hi, float* gmax_lo, void* stream) {
+                                  const float* group_bias, const float* residual, int act, float* out, float* out_hi,
+                                  float* out_lo, long long ldo, float* gmax, float* gmax_hi, float* gmax_lo,
+                                  void* stream) {
   using namespace ua;
   UA_REQUIRE(a_hi && a_lo && w_hi && w_lo, "ua_gemm_tf32x3_f32: NULL operand");
   UA_REQUIRE(M >= 1 && N >= 1 && K >= 1, "ua_gemm_tf32x3_f32: bad sizes M=%d N=%d K=%d", M, N, K);
@@ -485,7 +571,10 @@ extern "C" int ua_gemm_tf32x3_f32(const float* a_hi, const float* a_lo, long lon
   UA_REQUIRE(!(out || out_hi) || (ldo >= N && ldo % 4 == 0), "ua_gemm_tf32x3_f32: bad ldo");
   UA_REQUIRE(!gmax || M % 32 == 0, "ua_gemm_tf32x3_f32: the group max needs M %% 32 == 0");
   GemmParams p;
-  p.M = M, p.N = N, p.K = K, p.bias = bias, p.group_bias = group_bias, p.relu = relu;
+  UA_REQUIRE(act >= 0 && act <= 2, "ua_gemm_tf32x3_f32: act=%d (0 none, 1 relu, 2 gelu)", act);
+  UA_REQUIRE(!residual || ((uintptr_t)residual % 16 == 0 && ldo >= N && ldo % 4 == 0),
+             "ua_gemm_tf32x3_f32: residual must be 16-byte aligned with the outputs' leading dimension");
+  p.M = M, p.N = N, p.K = K, p.bias = bias, p.group_bias = group_bias, p.act = act, p.residual = residual;
   p.out = out, p.out_hi = out_hi, p.out_lo = out_lo, p.ldo = ldo, p.gmax = gmax, p.gmax_hi = gmax_hi, p.gmax_lo = gmax_lo;
   const bool wide = N % 256 == 0;
   const int bn = wide ? 256 : 128;

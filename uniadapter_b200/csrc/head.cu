@@ -1,7 +1,8 @@
 // Zero-shot cosine-logit head (SIMT path): L2-normalise, scale, dot with the text rows, softmax / entropy / argmax.
 // Replaces Uni_Adapter.py:21-26 (softmax_entropy) and :53-75 (get_logits_wrapper after the encoder call).
 // At batch 1 the op is a GEMV that streams the (K,D) text matrix once: one warp per class, float4 loads,
-// grid sized to cover the SMs; the batched tensor-core variant lives in head_tc.cu.
+// grid sized to cover the SMs. The batched variant (B >= 64) normalises and splits the rows here (ua_head_prepare_f32),
+// contracts them with the text rows on the tcgen05 GEMM (gemm_tf32x3.cu) and finishes with ua_row_stats_f32.
 #include "common.cuh"
 
 namespace ua {
@@ -87,14 +88,14 @@ __global__ void __launch_bounds__(256)
 
 // Per-row softmax, entropy -sum p*log(p+1e-10), first-index argmax.
 __global__ void __launch_bounds__(256)
-    row_stats_kernel(const float* __restrict__ logits, int K, float* __restrict__ prob, float* __restrict__ entropy,
-                     int* __restrict__ argmax) {
+    row_stats_kernel(const float* __restrict__ logits, int K, long long ld, float* __restrict__ prob,
+                     float* __restrict__ entropy, int* __restrict__ argmax) {
   __shared__ float s_f[8];
   __shared__ unsigned s_u[8];
   __shared__ float s_bcast[2];
   __shared__ unsigned s_arg;
   const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
-  const float* row = logits + (size_t)b * K;
+  const float* row = logits + (size_t)b * ld;
   // max + first argmax
   float mx = -INFINITY;
   unsigned mi = 0xffffffffu;
@@ -149,8 +150,39 @@ __global__ void __launch_bounds__(256)
 
 }  // namespace
 
-int launch_row_stats(const float* logits, int B, int K, float* prob, float* entropy, int* argmax, cudaStream_t st) {
-  row_stats_kernel<<<B, 256, 0, st>>>(logits, K, prob, entropy, argmax);
+// xnorm = x / |x| and the (hi, lo) tf32 pair of scale * xnorm (the A operand of the tensor-core head)
+__global__ void __launch_bounds__(256) l2norm_scale_split_kernel(const float* __restrict__ x, int D, float scale,
+                                                                 float* __restrict__ xnorm, float* __restrict__ hi,
+                                                                 float* __restrict__ lo) {
+  __shared__ float s_part[8];
+  const int b = blockIdx.x;
+  const float* row = x + (size_t)b * D;
+  float ss = 0.f;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const float v = __ldg(row + d);
+    ss = fmaf(v, v, ss);
+  }
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_part[w];
+  const float nrm = sqrtf(tot);
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const float xn = __fdiv_rn(__ldg(row + d), nrm);
+    xnorm[(size_t)b * D + d] = xn;
+    const float sv = __fmul_rn(scale, xn);            // the reference scales x before the contraction
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(sv));
+    const float h = __uint_as_float(r);
+    hi[(size_t)b * D + d] = h;
+    lo[(size_t)b * D + d] = sv - h;
+  }
+}
+
+int launch_row_stats(const float* logits, int B, int K, long long ld, float* prob, float* entropy, int* argmax,
+                     cudaStream_t st) {
+  row_stats_kernel<<<B, 256, 0, st>>>(logits, K, ld, prob, entropy, argmax);
   return check_launch("ua_head(row_stats)");
 }
 
@@ -181,6 +213,25 @@ extern "C" int ua_head_f32(const float* x, int B, int D, const float* text, int 
   logits_kernel<<<grid, W * 32, smem, st>>>(out_xnorm, B / num_text, D, text, K, scale, out_logits);
   rc = check_launch("ua_head_f32(logits)");
   if (rc != UA_OK) return rc;
-  if (out_prob || out_entropy || out_argmax) return launch_row_stats(out_logits, B, K, out_prob, out_entropy, out_argmax, st);
+  if (out_prob || out_entropy || out_argmax)
+    return launch_row_stats(out_logits, B, K, K, out_prob, out_entropy, out_argmax, st);
   return UA_OK;
+}
+
+extern "C" int ua_head_prepare_f32(const float* x, int B, int D, float scale, float* out_xnorm, float* out_hi, float* out_lo,
+                                   void* stream) {
+  using namespace ua;
+  UA_REQUIRE(x && out_xnorm && out_hi && out_lo, "ua_head_prepare_f32: NULL pointer");
+  UA_REQUIRE(B >= 0 && D >= 1, "ua_head_prepare_f32: bad sizes B=%d D=%d", B, D);
+  if (B == 0) return UA_OK;
+  l2norm_scale_split_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(x, D, scale, out_xnorm, out_hi, out_lo);
+  return check_launch("ua_head_prepare_f32");
+}
+
+extern "C" int ua_row_stats_f32(const float* logits, int B, int K, long long ld, float* out_prob, float* out_entropy,
+                                int32_t* out_argmax, void* stream) {
+  using namespace ua;
+  UA_REQUIRE(logits && B >= 0 && K >= 1 && ld >= K, "ua_row_stats_f32: bad arguments (B=%d K=%d ld=%lld)", B, K, ld);
+  if (B == 0) return UA_OK;
+  return launch_row_stats(logits, B, K, ld, out_prob, out_entropy, out_argmax, (cudaStream_t)stream);
 }

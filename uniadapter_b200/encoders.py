@@ -90,7 +90,13 @@ class _Block(nn.Module):
         self.mlp = _Mlp(dim, int(dim * mlp_ratio))
         self.attn = _Attention(dim, heads, qkv_bias)
 
-    def forward(self, x):
+    def forward(self, x, pos=None):
+        """``pos`` (the position embedding PointBERT re-adds before every block) is added first: blk(x + pos)."""
+        plan = getattr(self, '_tc_plan', None)
+        if plan is not None and x.is_cuda and not torch.is_grad_enabled():
+            return plan(x, pos)                              # fused tensor-core path (gemm.BlockPlan)
+        if pos is not None:
+            x = x + pos
         x = x + self.attn(self.norm1(x))
         return x + self.mlp(self.norm2(x))
 
@@ -117,7 +123,7 @@ class _PointBertTrunk(nn.Module):
         x = torch.cat((self.cls_token.expand(B, -1, -1), tokens), dim=1)
         pos = torch.cat((self.cls_pos.expand(B, -1, -1), self.pos_embed(center)), dim=1)
         for blk in self.blocks:
-            x = blk(x + pos)          # the reference re-adds the position embedding before every block
+            x = blk(x, pos)           # the reference re-adds the position embedding before every block: blk(x + pos)
         x = self.norm(x)
         return torch.cat([x[:, 0], x[:, 1:].max(1)[0]], dim=-1)
 
@@ -267,10 +273,12 @@ def use_tensor_cores(model: nn.Module, flag: bool = True, linears: bool = True) 
     """Attach (or drop) the tcgen05 3xTF32 plans (gemm.py): the mini-PointNet group encoder and, with ``linears``, the
     nn.Linear layers whose shapes the GEMM supports (N % 128 == 0, K % 32 == 0). Inference only; weights are folded
     and split when this is called, so call it again after loading other weights."""
-    from .gemm import GroupEncoderPlan, LinearPlan
+    from .gemm import BlockPlan, GroupEncoderPlan, LinearPlan
     for mod in model.modules():
         if isinstance(mod, MiniPointNet):
             mod._tc_plan = GroupEncoderPlan(mod) if flag else None
+        elif isinstance(mod, _Block) and linears:
+            mod._tc_plan = BlockPlan(mod) if (flag and BlockPlan.supported(mod)) else None
         elif isinstance(mod, nn.Linear) and linears:
             mod._tc_plan = LinearPlan(mod) if (flag and LinearPlan.supported(mod)) else None
     return model

@@ -16,9 +16,27 @@ def split_tf32(x: torch.Tensor):
     return hi, lo
 
 
+_ACT = {None: 0, 'none': 0, 'relu': 1, 'gelu': 2}
+
+
+def layernorm_split(x, ln, pos=None, want_sum=False):
+    """(hi, lo) of ``ln(x + pos)`` over the last dimension; with ``want_sum`` also returns ``x + pos``."""
+    x = x.contiguous()
+    C = x.shape[-1]
+    rows = x.numel() // C
+    hi, lo = torch.empty_like(x), torch.empty_like(x)
+    s = torch.empty_like(x) if want_sum else None
+    rc = _lib.lib().ua_layernorm_split_f32(_lib.ptr(x), _lib.ptr(pos.contiguous()) if pos is not None else None,
+                                          _lib.ptr(ln.weight), _lib.ptr(ln.bias), float(ln.eps), rows, C, _lib.ptr(s),
+                                          _lib.ptr(hi), _lib.ptr(lo), _lib.stream_ptr())
+    _lib.check(rc, "ua_layernorm_split_f32")
+    return ((hi, lo), s) if want_sum else (hi, lo)
+
+
 def gemm_tf32x3(a, w, bias=None, group_bias=None, relu=False, out=False, out_split=False, group_max=False,
-                group_max_split=False):
-    """a = (a_hi, a_lo) [M,K]; w = (w_hi, w_lo) [N,K]. Returns a dict with the requested outputs:
+                group_max_split=False, act=None, residual=None):
+    """a = (a_hi, a_lo) [M,K]; w = (w_hi, w_lo) [N,K]; epilogue + bias [N] + group_bias [M/32,N] + residual [M,N], then
+    ReLU / erf-GELU (``act``). Returns a dict with the requested outputs:
     'out' [M,N] fp32, 'out_split' (hi, lo), 'gmax' [M/32,N], 'gmax_split' (hi, lo)."""
     a_hi, a_lo = a
     w_hi, w_lo = w
@@ -34,7 +52,8 @@ def gemm_tf32x3(a, w, bias=None, group_bias=None, relu=False, out=False, out_spl
     gl = torch.empty_like(gm) if group_max_split else None
     rc = _lib.lib().ua_gemm_tf32x3_f32(
         _lib.ptr(a_hi), _lib.ptr(a_lo), a_hi.stride(0), _lib.ptr(w_hi), _lib.ptr(w_lo), w_hi.stride(0), M, N, K,
-        _lib.ptr(bias), _lib.ptr(group_bias), int(bool(relu)), _lib.ptr(o), _lib.ptr(oh), _lib.ptr(ol), N, _lib.ptr(gm),
+        _lib.ptr(bias), _lib.ptr(group_bias), _lib.ptr(residual), 1 if relu else _ACT[act], _lib.ptr(o), _lib.ptr(oh),
+        _lib.ptr(ol), N, _lib.ptr(gm),
         _lib.ptr(gh), _lib.ptr(gl), _lib.stream_ptr())
     _lib.check(rc, "ua_gemm_tf32x3_f32")
     if out:
@@ -133,3 +152,36 @@ class LinearPlan:
         lead = x.shape[:-1]
         a = split_tf32(x.reshape(-1, self.K))
         return gemm_tf32x3(a, self.w, bias=self.b, relu=relu, out=True)['out'].reshape(*lead, self.N)
+
+
+class BlockPlan:
+    """A pre-LN transformer block with every dense layer on the tensor-core GEMM and the element-wise work fused around
+    it: (x + pos, LayerNorm, split) in one kernel, the skip connections in the proj / fc2 epilogues, GELU + split in the
+    fc1 epilogue. Attention itself stays torch SDPA (the north star keeps it in PyTorch)."""
+
+    def __init__(self, block):
+        self.block = block
+        self.qkv, self.proj = LinearPlan(block.attn.qkv), LinearPlan(block.attn.proj)
+        self.fc1, self.fc2 = LinearPlan(block.mlp.fc1), LinearPlan(block.mlp.fc2)
+
+    @staticmethod
+    def supported(block) -> bool:
+        dims_ok = block.norm1.normalized_shape[0] % 128 == 0 and block.norm1.normalized_shape[0] <= 1024
+        return dims_ok and all(LinearPlan.supported(l) for l in (block.attn.qkv, block.attn.proj, block.mlp.fc1, block.mlp.fc2))
+
+    @torch.no_grad()
+    def __call__(self, x, pos=None):
+        import torch.nn.functional as F
+        blk = self.block
+        B, N, C = x.shape
+        H = blk.attn.heads
+        h, xs = layernorm_split(x, blk.norm1, pos, want_sum=True) if pos is not None else (layernorm_split(x, blk.norm1), x)
+        flat = lambda pair: (pair[0].view(B * N, -1), pair[1].view(B * N, -1))
+        qkv = gemm_tf32x3(flat(h), self.qkv.w, bias=self.qkv.b, out=True)['out']
+        q, k, v = qkv.view(B, N, 3, H, C // H).permute(2, 0, 3, 1, 4)
+        a = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B * N, C)
+        x1 = gemm_tf32x3(split_tf32(a), self.proj.w, bias=self.proj.b, residual=xs.view(B * N, C), out=True)['out']
+        h2 = layernorm_split(x1, blk.norm2)
+        g = gemm_tf32x3(h2, self.fc1.w, bias=self.fc1.b, act='gelu', out_split=True)['out_split']
+        x2 = gemm_tf32x3(g, self.fc2.w, bias=self.fc2.b, residual=x1, out=True)['out']
+        return x2.view(B, N, C)

@@ -32,6 +32,43 @@ def zero_shot_head(x: torch.Tensor, text: torch.Tensor, scale: float = 100.0, *,
     return xnorm, logits, entropy, prob, argmax
 
 
+class HeadPlan:
+    """The head as a dense contraction on the tcgen05 GEMM for batched inputs (B >= 64, BASELINE cfg 5): the text rows
+    are padded to a multiple of 128 classes and split into (hi, lo) once; per call: normalise + scale + split the rows,
+    one GEMM, softmax / entropy / argmax over the first K columns. Same outputs as :func:`zero_shot_head`."""
+
+    def __init__(self, text: torch.Tensor, scale: float = 100.0):
+        from .gemm import split_tf32
+        text = text.float().contiguous()
+        self.K, self.D = text.shape
+        if self.D % 32:
+            raise _lib.UaError(f"HeadPlan: feature dim {self.D} must be a multiple of 32")
+        self.Kpad = -(-self.K // 128) * 128
+        padded = torch.zeros(self.Kpad, self.D, dtype=torch.float32, device=text.device)
+        padded[:self.K] = text
+        self.text = split_tf32(padded)
+        self.scale = float(scale)
+
+    @torch.no_grad()
+    def __call__(self, x: torch.Tensor, want_prob: bool = True):
+        from .gemm import gemm_tf32x3
+        x = x.float().contiguous()
+        B, D = x.shape
+        dev = x.device
+        xnorm, hi, lo = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+        rc = _lib.lib().ua_head_prepare_f32(_lib.ptr(x), B, D, self.scale, _lib.ptr(xnorm), _lib.ptr(hi), _lib.ptr(lo),
+                                           _lib.stream_ptr())
+        _lib.check(rc, "ua_head_prepare_f32")
+        padded = gemm_tf32x3((hi, lo), self.text, out=True)['out']                      # (B, Kpad)
+        prob = torch.empty((B, self.K), dtype=torch.float32, device=dev) if want_prob else None
+        entropy = torch.empty((B,), dtype=torch.float32, device=dev)
+        argmax = torch.empty((B,), dtype=torch.int32, device=dev)
+        rc = _lib.lib().ua_row_stats_f32(_lib.ptr(padded), B, self.K, self.Kpad, _lib.ptr(prob), _lib.ptr(entropy),
+                                        _lib.ptr(argmax), _lib.stream_ptr())
+        _lib.check(rc, "ua_row_stats_f32")
+        return xnorm, padded[:, :self.K], entropy, prob, argmax
+
+
 def _as_text_rows(clip_weights: torch.Tensor, feat_dim: int) -> torch.Tensor:
     """Accept the reference's (D,K) ``clip_weights`` (or a (K,D) text matrix) and return (K,D) rows."""
     if clip_weights.shape[0] == feat_dim and clip_weights.shape[1] != feat_dim:
