@@ -14,10 +14,12 @@
 //   warp 1     TMEM allocation; one elected lane issues tcgen05.mma (M=128, N=BN, K=8 per instruction, 12 per
 //              k-block), tcgen05.commit releases the smem stage / publishes the accumulator
 //   warps 2-5  epilogue: tcgen05.ld of the accumulator (one row per thread, 32 columns per load), bias / per-row-group
-//              bias / ReLU, then any of: fp32 store, (hi, lo) store, max over each group of 32 consecutive rows
-//              (= one warp's TMEM lanes: the max over the 32 points of a point group)
+//              bias / residual / ReLU / GELU, then any of: fp32 tile, (hi, lo) tiles — staged in 128B-swizzled shared
+//              memory and written by TMA stores (full lines instead of 32 partial lines per instruction) — and the max
+//              over each group of 32 consecutive rows (= one warp's TMEM lanes: the 32 points of a point group)
 //   two accumulator stages in TMEM (2 x BN <= 512 columns): the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <cuda.h>
+#include <string.h>
 #include "common.cuh"
 
 namespace ua {
@@ -66,6 +68,13 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
           smem_u32(dst)),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+// shared -> global tile store through the TMA unit (bulk async-group completion); rows beyond the tensor are clipped
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -148,21 +157,25 @@ struct SmemLayout {
   static constexpr int kABytes = kBM * kBK * 4;       // 16 KB
   static constexpr int kBBytes = BN * kBK * 4;
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+  static constexpr int kStoreBytes = 4 * 4096;        // one 32 x 32 fp32 staging tile per epilogue warp (TMA store)
   static constexpr int kBiasBytes = 4 * BN * 4;       // one effective bias row per epilogue warp
-  static constexpr int kTotal = STAGES * kStageBytes + kBiasBytes + 1024 /* alignment slack */ + 256 /* barriers */;
+  static constexpr int kTotal =
+      STAGES * kStageBytes + kStoreBytes + kBiasBytes + 1024 /* alignment slack */ + 256 /* barriers */;
 };
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(kGemmThreads, 1)
     gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                        const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
-                       const GemmParams p) {
+                       const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_out_hi,
+                       const __grid_constant__ CUtensorMap map_out_lo, const GemmParams p) {
   using L = SmemLayout<BN, STAGES>;
   extern __shared__ unsigned char s_raw[];
   // 128B-swizzled tiles need 1024-byte alignment
   unsigned char* s_tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(s_raw) + 1023) & ~(uintptr_t)1023);
-  float* s_bias = reinterpret_cast<float*>(s_tiles + STAGES * L::kStageBytes);           // [4 warps][BN]
-  uint64_t* s_full = reinterpret_cast<uint64_t*>(s_tiles + STAGES * L::kStageBytes + L::kBiasBytes);   // [STAGES]
+  unsigned char* s_store = s_tiles + STAGES * L::kStageBytes;                             // [4 warps][4096], 1024-aligned
+  float* s_bias = reinterpret_cast<float*>(s_store + L::kStoreBytes);                     // [4 warps][BN]
+  uint64_t* s_full = reinterpret_cast<uint64_t*>(s_store + L::kStoreBytes + L::kBiasBytes);   // [STAGES]
   uint64_t* s_empty = s_full + STAGES;                                                   // [STAGES]
   uint64_t* s_tfull = s_empty + STAGES;                                                  // [2]
   uint64_t* s_tempty = s_tfull + 2;                                                      // [2]
@@ -174,6 +187,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 
   if (warp == 0 && elect_one()) {
     prefetch_tmap(&map_a_hi), prefetch_tmap(&map_a_lo), prefetch_tmap(&map_w_hi), prefetch_tmap(&map_w_lo);
+    if (p.out) prefetch_tmap(&map_out);
+    if (p.out_hi) prefetch_tmap(&map_out_hi), prefetch_tmap(&map_out_lo);
     for (int i = 0; i < STAGES; ++i) mbar_init(&s_full[i], 1), mbar_init(&s_empty[i], 1);
     for (int i = 0; i < 2; ++i) mbar_init(&s_tfull[i], 1), mbar_init(&s_tempty[i], 4);
     fence_mbar_init();
@@ -250,6 +265,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       // tile are still running: the chunk loop below then reads it with broadcast loads instead of stalling on HBM
       const bool has_bias = p.bias != nullptr || p.group_bias != nullptr;
       float* my_bias = s_bias + (warp - 2) * BN;
+      unsigned char* my_store = s_store + (warp - 2) * 4096;
       if (has_bias) {
         const bool grp_ok = p.group_bias != nullptr && m_idx + quarter * 32 < p.M;
 #pragma unroll
@@ -293,23 +309,37 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0.5f * v[i] * (1.0f + erff(v[i] * 0.70710678118654752f));
         }
-        if (p.out && row_ok) {
-          float4* o = reinterpret_cast<float4*>(p.out + (size_t)row * p.ldo + col);
+        // outputs leave through shared memory and the TMA unit: a thread owns one row, so direct stores would touch 32
+        // different lines per instruction; the staged tile (128B-swizzled, conflict-free quarter-warp writes) goes out
+        // as full lines. One 4 KB staging tile per warp, reused once the previous store has read it.
+        const int row0 = m_idx + quarter * 32;
+        auto stage_and_store = [&](const CUtensorMap* map, const float (&t)[32]) {
+          if (lane == 0) bulk_wait_read<0>();
+          __syncwarp();
+          const uint32_t base = smem_u32(my_store) + (uint32_t)lane * 128u;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        }
-        if (p.out_hi && row_ok) {
-          float4* oh = reinterpret_cast<float4*>(p.out_hi + (size_t)row * p.ldo + col);
-          float4* ol = reinterpret_cast<float4*>(p.out_lo + (size_t)row * p.ldo + col);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float4 h, l;
-            h.x = tf32_round(v[4 * i]), l.x = v[4 * i] - h.x;
-            h.y = tf32_round(v[4 * i + 1]), l.y = v[4 * i + 1] - h.y;
-            h.z = tf32_round(v[4 * i + 2]), l.z = v[4 * i + 2] - h.z;
-            h.w = tf32_round(v[4 * i + 3]), l.w = v[4 * i + 3] - h.w;
-            oh[i] = h, ol[i] = l;
+          for (int c = 0; c < 8; ++c) {
+            const uint32_t addr = base + ((uint32_t)(c ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(t[4 * c]), "f"(t[4 * c + 1]),
+                         "f"(t[4 * c + 2]), "f"(t[4 * c + 3])
+                         : "memory");
           }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(map, my_store, col, row0);
+            bulk_commit();
+          }
+        };
+        if (p.out && row0 < p.M) stage_and_store(&map_out, v);
+        if (p.out_hi && row0 < p.M) {
+          float h[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) h[i] = tf32_round(v[i]);
+          stage_and_store(&map_out_hi, h);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) h[i] = v[i] - h[i];
+          stage_and_store(&map_out_lo, h);
         }
         if (p.gmax) {
           // max over the warp's 32 rows (one point group), one REDUX per column; lane i keeps column i
@@ -334,6 +364,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       if (lane == 0) mbar_arrive(&s_tempty[acc]);
       if (++acc == 2) acc = 0, acc_phase ^= 1u;
     }
+    if (lane == 0) bulk_wait<0>();     // this warp's tile stores are complete before the CTA retires
   }
   tc_fence_before();
   __syncthreads();
@@ -464,6 +495,8 @@ EncodeTiledFn encode_fn() {
 
 // 2-D fp32 tensor [rows, cols] with row pitch ld (elements), box [box_rows x 32 columns], 128B swizzle, zero fill
 int make_map(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_rows) {
+  memset(map, 0, sizeof(*map));
+  if (!base) return UA_OK;             // unused output: the kernel never touches this map
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     set_error("ua_gemm_tf32x3_f32: cuTensorMapEncodeTiled is not available from the driver");
@@ -486,7 +519,8 @@ int make_map(CUtensorMap* map, const float* base, long long rows, long long cols
 
 template <int BN, int STAGES>
 int launch_gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo,
-                const GemmParams& p, cudaStream_t st) {
+                const CUtensorMap& o, const CUtensorMap& o_hi, const CUtensorMap& o_lo, const GemmParams& p,
+                cudaStream_t st) {
   using L = SmemLayout<BN, STAGES>;
   auto kern = gemm_tf32x3_kernel<BN, STAGES>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
@@ -496,7 +530,7 @@ int launch_gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensor
   }
   const int tiles = ((p.M + kBM - 1) / kBM) * (p.N / BN);
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-  kern<<<grid, kGemmThreads, L::kTotal, st>>>(a_hi, a_lo, w_hi, w_lo, p);
+  kern<<<grid, kGemmThreads, L::kTotal, st>>>(a_hi, a_lo, w_hi, w_lo, o, o_hi, o_lo, p);
   return check_launch("ua_gemm_tf32x3_f32");
 }
 
@@ -569,6 +603,8 @@ extern "C" int ua_gemm_tf32x3_f32(const float* a_hi, const float* a_lo, long lon
              "ua_gemm_tf32x3_f32: gmax_hi / gmax_lo come as a pair, with gmax");
   UA_REQUIRE(out || out_hi || gmax, "ua_gemm_tf32x3_f32: no output requested");
   UA_REQUIRE(!(out || out_hi) || (ldo >= N && ldo % 4 == 0), "ua_gemm_tf32x3_f32: bad ldo");
+  UA_REQUIRE((uintptr_t)out % 16 == 0 && (uintptr_t)out_hi % 16 == 0 && (uintptr_t)out_lo % 16 == 0,
+             "ua_gemm_tf32x3_f32: outputs must be 16-byte aligned");
   UA_REQUIRE(!gmax || M % 32 == 0, "ua_gemm_tf32x3_f32: the group max needs M %% 32 == 0");
   GemmParams p;
   UA_REQUIRE(act >= 0 && act <= 2, "ua_gemm_tf32x3_f32: act=%d (0 none, 1 relu, 2 gelu)", act);
@@ -584,7 +620,12 @@ extern "C" int ua_gemm_tf32x3_f32(const float* a_hi, const float* a_lo, long lon
   if ((rc = make_map(&m_a_lo, a_lo, M, K, lda, kBM)) != UA_OK) return rc;
   if ((rc = make_map(&m_w_hi, w_hi, N, K, ldw, bn)) != UA_OK) return rc;
   if ((rc = make_map(&m_w_lo, w_lo, N, K, ldw, bn)) != UA_OK) return rc;
+  // output tiles of 32 rows x 32 columns (128-byte rows, 128B swizzle) for the staged TMA stores
+  CUtensorMap m_o, m_o_hi, m_o_lo;
+  if ((rc = make_map(&m_o, out, M, N, ldo, 32)) != UA_OK) return rc;
+  if ((rc = make_map(&m_o_hi, out_hi, M, N, ldo, 32)) != UA_OK) return rc;
+  if ((rc = make_map(&m_o_lo, out_lo, M, N, ldo, 32)) != UA_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  return wide ? launch_gemm<256, 2>(m_a_hi, m_a_lo, m_w_hi, m_w_lo, p, st)
-              : launch_gemm<128, 3>(m_a_hi, m_a_lo, m_w_hi, m_w_lo, p, st);
+  return wide ? launch_gemm<256, 2>(m_a_hi, m_a_lo, m_w_hi, m_w_lo, m_o, m_o_hi, m_o_lo, p, st)
+              : launch_gemm<128, 3>(m_a_hi, m_a_lo, m_w_hi, m_w_lo, m_o, m_o_hi, m_o_lo, p, st);
 }
