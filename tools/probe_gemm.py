@@ -9,6 +9,8 @@ shapes = [(128, 128, 32), (128, 256, 32), (256, 128, 64), (128, 128, 128), (4096
           (7695, 384, 1536)]
 if len(sys.argv) > 1:
     shapes = shapes[:int(sys.argv[1])]
+from uniadapter_b200 import _lib
+bns = [int(b) for b in os.environ.get("GEMM_BNS", "0").split(",")]
 for (M, N, K) in shapes:
     a = torch.randn(M, K, device=dev)
     w = torch.randn(N, K, device=dev) / K ** 0.5
@@ -30,6 +32,18 @@ for (M, N, K) in shapes:
         gemm_tf32x3(ap, wp, bias=bias, out=True)
     e.record(); torch.cuda.synchronize()
     us = s.elapsed_time(e) / 5 * 1e3
+    for bn in bns:
+        if bn and N % bn:
+            continue
+        _lib.set_tuning("gemm_bn", bn)
+        for _ in range(2):
+            gemm_tf32x3(ap, wp, bias=bias, out=True)
+        s.record()
+        for _ in range(5):
+            gemm_tf32x3(ap, wp, bias=bias, out=True)
+        e.record(); torch.cuda.synchronize()
+        print(f"      bn={bn:3d}: {s.elapsed_time(e) / 5 * 1e3:8.1f} us")
+    _lib.set_tuning("gemm_bn", 0)
     s.record()
     for _ in range(5):
         torch.addmm(bias, a, w.t())

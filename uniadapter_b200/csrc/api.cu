@@ -13,6 +13,7 @@ extern int g_fps_threads;
 extern int g_knn_warps;
 extern int g_modedota_threads;
 extern int g_modedota_v;
+extern int g_gemm_bn;
 extern int g_modedota_groups;
 extern int g_modedota_logprod;
 
@@ -48,6 +49,7 @@ extern "C" int ua_set_tuning(const char* key, int value) {
   if (!strcmp(key, "knn_warps")) { ua::g_knn_warps = value; return UA_OK; }
   if (!strcmp(key, "modedota_threads")) { ua::g_modedota_threads = value; return UA_OK; }
   if (!strcmp(key, "modedota_groups")) { ua::g_modedota_groups = value; return UA_OK; }
+  if (!strcmp(key, "gemm_bn")) { ua::g_gemm_bn = value; return UA_OK; }
   if (!strcmp(key, "modedota_v")) { ua::g_modedota_v = value; return UA_OK; }
   if (!strcmp(key, "modedota_logprod")) { ua::g_modedota_logprod = value; return UA_OK; }
   ua::set_error("ua_set_tuning: unknown key '%s'", key);

@@ -23,6 +23,9 @@
 #include "common.cuh"
 
 namespace ua {
+
+int g_gemm_bn = 0;   // tuning override: force the N tile (128, 192 or 256)
+
 namespace {
 
 constexpr int kBM = 128;         // rows per tile (UMMA M)
@@ -193,7 +196,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     for (int i = 0; i < 2; ++i) mbar_init(&s_tfull[i], 1), mbar_init(&s_tempty[i], 4);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(s_tmem, 2 * BN);     // 2 accumulator stages of BN fp32 columns (power of two >= 32)
+  constexpr uint32_t kTmemCols = 2 * BN <= 256 ? 256u : 512u;   // 2 accumulator stages of BN fp32 columns, power of two
+  if (warp == 1) tmem_alloc(s_tmem, kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -368,7 +372,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 // hi = tf32(x) (round to nearest, low 13 bits zero), lo = x - hi
@@ -612,8 +616,23 @@ extern "C" int ua_gemm_tf32x3_f32(const float* a_hi, const float* a_lo, long lon
              "ua_gemm_tf32x3_f32: residual must be 16-byte aligned with the outputs' leading dimension");
   p.M = M, p.N = N, p.K = K, p.bias = bias, p.group_bias = group_bias, p.act = act, p.residual = residual;
   p.out = out, p.out_hi = out_hi, p.out_lo = out_lo, p.ldo = ldo, p.gmax = gmax, p.gmax_hi = gmax_hi, p.gmax_lo = gmax_lo;
-  const bool wide = N % 256 == 0;
-  const int bn = wide ? 256 : 128;
+  // N tile: among the sizes that divide N, the one with the least (waves over the 148 SMs) x (tile width); wider wins
+  // ties (fewer, larger MMAs and less A traffic per flop). The kernel is bound by L2 -> shared-memory operand traffic
+  // (3xTF32 streams four operand tiles per k-block), so a single-wave N=192 tiling of N=384 does not beat two waves of
+  // N=128 (measured: 60.8 vs 58.4 us at 7695 x 384 x 1536).
+  int bn = 0;
+  {
+    const long long m_tiles = (M + kBM - 1) / kBM;
+    long long best = 0;
+    for (int cand : {256, 192, 128}) {
+      if (N % cand) continue;
+      if (g_gemm_bn > 0 ? cand != g_gemm_bn : cand == 192) continue;   // 192 only on request: never faster when measured
+      const long long waves = (m_tiles * (N / cand) + kNumSMs - 1) / kNumSMs;
+      const long long cost = waves * cand;
+      if (!bn || cost < best) bn = cand, best = cost;
+    }
+    UA_UNSUPPORTED(!bn, "ua_gemm_tf32x3_f32: no N tile for N=%d (gemm_bn=%d)", N, g_gemm_bn);
+  }
   CUtensorMap m_a_hi, m_a_lo, m_w_hi, m_w_lo;
   int rc;
   if ((rc = make_map(&m_a_hi, a_hi, M, K, lda, kBM)) != UA_OK) return rc;
@@ -626,6 +645,7 @@ extern "C" int ua_gemm_tf32x3_f32(const float* a_hi, const float* a_lo, long lon
   if ((rc = make_map(&m_o_hi, out_hi, M, N, ldo, 32)) != UA_OK) return rc;
   if ((rc = make_map(&m_o_lo, out_lo, M, N, ldo, 32)) != UA_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  return wide ? launch_gemm<256, 2>(m_a_hi, m_a_lo, m_w_hi, m_w_lo, m_o, m_o_hi, m_o_lo, p, st)
-              : launch_gemm<128, 3>(m_a_hi, m_a_lo, m_w_hi, m_w_lo, m_o, m_o_hi, m_o_lo, p, st);
+  if (bn == 256) return launch_gemm<256, 2>(m_a_hi, m_a_lo, m_w_hi, m_w_lo, m_o, m_o_hi, m_o_lo, p, st);
+  if (bn == 192) return launch_gemm<192, 2>(m_a_hi, m_a_lo, m_w_hi, m_w_lo, m_o, m_o_hi, m_o_lo, p, st);
+  return launch_gemm<128, 3>(m_a_hi, m_a_lo, m_w_hi, m_w_lo, m_o, m_o_hi, m_o_lo, p, st);
 }
