@@ -34,6 +34,9 @@ def parse_args(argv=None):
     p.add_argument('--output-dir', type=str, default='./outputs')
     p.add_argument('--vlm3d', type=str, default='uni3d', choices=['uni3d', 'ulip', 'openshape'])
     p.add_argument('--precomputed-text-features', type=str, default=None)
+    p.add_argument('--myroot', type=str, default=None,
+                   help='directory with data_{corruption}_{severity}.npy + label.npy (reference layout); synthetic '
+                        'streams when absent')
     p.add_argument('--dataset_name', type=str, default='modelnet')
     p.add_argument('--validate_dataset_name', type=str, default='modelnet40_openshape')
     p.add_argument('--batch-size', type=int, default=1)
@@ -71,7 +74,7 @@ def main(argv=None):
     from uniadapter_b200 import parallel
     from uniadapter_b200.adapter import test_zeroshot_3d_core
     from uniadapter_b200.encoders import build_encoder
-    from uniadapter_b200.streams import CORRUPTIONS, SyntheticStream, synthetic_text_features
+    from uniadapter_b200.streams import CORRUPTIONS, NpyCorruptionStream, SyntheticStream, synthetic_text_features
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -107,8 +110,11 @@ def main(argv=None):
         corr = corruptions[s]
         args.corruption = corr
         logging.info(f"\n{'=' * 20} Processing Corruption: {corr} {'=' * 20}")
-        dataset = SyntheticStream(args.stream_length, args.npoints, args.num_classes, seed=args.seed, stream=s,
-                                  colored=(args.vlm3d == 'openshape'))
+        if args.myroot:      # the reference's corruption files (data/tta_datasets.py:11-36), memory-mapped
+            dataset = NpyCorruptionStream(args.myroot, corr, args.severity, npoints=args.npoints)
+        else:
+            dataset = SyntheticStream(args.stream_length, args.npoints, args.num_classes, seed=args.seed, stream=s,
+                                      colored=(args.vlm3d == 'openshape'))
         loader = torch.utils.data.DataLoader(dataset, batch_size=args.batch_size, shuffle=False, num_workers=args.workers,
                                              pin_memory=True, drop_last=False)
         result = test_zeroshot_3d_core(test_loader=loader, validate_dataset_name=args.validate_dataset_name, model=model,
