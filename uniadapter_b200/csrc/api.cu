@@ -14,6 +14,8 @@ extern int g_knn_warps;
 extern int g_modedota_threads;
 extern int g_modedota_v;
 extern int g_gemm_bn;
+extern int g_resid_cb;
+extern int g_resid_dbl;
 extern int g_modedota_groups;
 extern int g_modedota_logprod;
 
@@ -49,6 +51,8 @@ extern "C" int ua_set_tuning(const char* key, int value) {
   if (!strcmp(key, "knn_warps")) { ua::g_knn_warps = value; return UA_OK; }
   if (!strcmp(key, "modedota_threads")) { ua::g_modedota_threads = value; return UA_OK; }
   if (!strcmp(key, "modedota_groups")) { ua::g_modedota_groups = value; return UA_OK; }
+  if (!strcmp(key, "resid_cb")) { ua::g_resid_cb = value; return UA_OK; }
+  if (!strcmp(key, "resid_dbl")) { ua::g_resid_dbl = value; return UA_OK; }
   if (!strcmp(key, "gemm_bn")) { ua::g_gemm_bn = value; return UA_OK; }
   if (!strcmp(key, "modedota_v")) { ua::g_modedota_v = value; return UA_OK; }
   if (!strcmp(key, "modedota_logprod")) { ua::g_modedota_logprod = value; return UA_OK; }

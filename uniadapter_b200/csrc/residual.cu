@@ -21,10 +21,14 @@
 #include "common.cuh"
 
 namespace ua {
+
+int g_resid_cb = 0;    // tuning: classes per CTA of the forward kernel (0 = heuristic)
+int g_resid_dbl = 0;   // tuning: floats per lane of the backward kernel (1 or 2; 0 = heuristic)
+
 namespace {
 
-constexpr int kRI = 4;    // rows per register tile (forward)
-constexpr int kCJ = 5;    // columns per register tile (forward)
+constexpr int kRI = 5;    // rows per register tile (forward)
+constexpr int kCJ = 4;    // columns per register tile (forward)
 constexpr int kBR = 5;    // rows per register tile (backward)
 constexpr int kThreads = 256;
 
@@ -143,7 +147,7 @@ struct FwdParams {
   float eps;
 };
 
-__global__ void __launch_bounds__(kThreads, 1) resid_forward_kernel(const FwdParams p) {
+__global__ void __launch_bounds__(kThreads, 3) resid_forward_kernel(const FwdParams p) {
   extern __shared__ __align__(16) float s_f[];
   const int K = p.K, M = p.M, D = p.D;
   const int s = blockIdx.y, k0 = blockIdx.x * p.CB;
@@ -171,11 +175,14 @@ __global__ void __launch_bounds__(kThreads, 1) resid_forward_kernel(const FwdPar
   const float* Xs = p.X + (size_t)s * K * D;
   const float* cst = p.consts + ((size_t)s * K + k0) * M * 2;
   const int ncg = (ncols + kCJ - 1) / kCJ, nrg = (K + kRI - 1) / kRI;
-  for (int cg = warp; cg < ncg; cg += kThreads / 32) {
+  // (column group, row group) register tiles are dealt round-robin to the warps: a CTA holds only a few classes, so
+  // that several CTAs are resident per SM and hide each other's shared-memory / L2 latency
+  for (int item = warp; item < ncg * nrg; item += kThreads / 32) {
+    const int cg = item / nrg, rg = item - cg * nrg;
     int col[kCJ];
 #pragma unroll
     for (int c = 0; c < kCJ; ++c) col[c] = min(cg * kCJ + c, ncols - 1);
-    for (int rg = 0; rg < nrg; ++rg) {
+    {
       int rowi[kRI];
 #pragma unroll
       for (int r = 0; r < kRI; ++r) rowi[r] = min(rg * kRI + r, K - 1);
@@ -321,7 +328,7 @@ struct BwdParams {
 };
 
 template <int DBL>   // floats per lane along D; the CTA owns a 32*DBL-wide slice of D
-__global__ void __launch_bounds__(kThreads, 1) resid_backward_kernel(const BwdParams p) {
+__global__ void __launch_bounds__(kThreads, DBL == 1 ? 2 : 1) resid_backward_kernel(const BwdParams p) {
   extern __shared__ __align__(16) float s_b[];
   constexpr int DB = 32 * DBL;
   const int K = p.K, M = p.M, D = p.D, ncols = K * M;
@@ -400,21 +407,29 @@ int make_plan(int S, int K, int M, int D, Plan& pl) {
   UA_UNSUPPORTED(M % 4 != 0 || M > 16, "residual learning: M=%d must be 4, 8, 12 or 16", M);
   UA_UNSUPPORTED(K > 128, "residual learning: K=%d > 128 (the likelihood matrix is kept in shared memory)", K);
   const size_t budget = 220 * 1024;
-  // forward: CB classes per CTA, tiles 2*CB*M*D floats + lj K*CB*M floats
-  int cbmax = (int)((budget / 4) / ((size_t)2 * M * D + (size_t)K * M));
+  // forward: CB classes per CTA, tiles 2*CB*M*D floats + lj K*CB*M floats. One class per CTA on purpose: several small
+  // CTAs per SM hide latency far better than one fat CTA with eight warps (measured at S=15, K=40: 10 Adam steps take
+  // 872 us with CB=1, 940 with CB=2, 1015 with CB=5).
+  const size_t per_class = ((size_t)2 * M * D + (size_t)K * M) * sizeof(float);
+  int cbmax = (int)(budget / per_class);
   UA_UNSUPPORTED(cbmax < 1, "residual learning: M*D=%d does not fit in shared memory", M * D);
-  if (cbmax > K) cbmax = K;
-  int nblk = (K + cbmax - 1) / cbmax;
-  while (nblk < K && (long long)S * (nblk + 1) <= kNumSMs) ++nblk;   // spread over the SMs while it stays one wave
-  pl.CB = (K + nblk - 1) / nblk;
+  int cb = 1;
+  if (g_resid_cb > 0) cb = g_resid_cb;
+  if (cb > cbmax) cb = cbmax;
+  if (cb > K) cb = K;
+  pl.CB = cb;
   pl.nblk = (K + pl.CB - 1) / pl.CB;
   pl.smem_fwd = ((size_t)2 * pl.CB * M * D + (size_t)K * pl.CB * M) * sizeof(float);
   pl.smem_loss = ((size_t)2 * K * K + 3 * K) * sizeof(float);
-  // backward: the widest D slice whose K*M columns fit
+  // backward: the D slice (32 or 64 wide) whose K*M columns fit; the narrow slice when that makes two CTAs resident
   pl.DBL = 0;
   for (int dbl = 2; dbl >= 1 && !pl.DBL; --dbl)
     if ((size_t)2 * K * M * 32 * dbl * sizeof(float) <= budget && D % (32 * dbl) == 0) pl.DBL = dbl;
   UA_UNSUPPORTED(!pl.DBL, "residual learning: K*M=%d columns do not fit in shared memory", K * M);
+  if (pl.DBL == 2 && (size_t)2 * K * M * 32 * sizeof(float) <= budget / 2) pl.DBL = 1;   // two CTAs resident per SM
+  if (g_resid_dbl == 1 || g_resid_dbl == 2) {
+    if ((size_t)2 * K * M * 32 * g_resid_dbl * sizeof(float) <= budget && D % (32 * g_resid_dbl) == 0) pl.DBL = g_resid_dbl;
+  }
   pl.NB = D / (32 * pl.DBL);
   pl.smem_bwd = (size_t)2 * K * M * 32 * pl.DBL * sizeof(float);
   return UA_OK;
