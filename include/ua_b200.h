@@ -199,6 +199,20 @@ int ua_layernorm_split_f32(const float* x, const float* pos, const float* gamma,
                            long long rows, int C, float* out_sum, float* out_hi, float* out_lo, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * fp32-accurate multi-head self-attention on tcgen05 (3xTF32), head dimension 64:
+ *   O = softmax(Q K^T / 8) V  per (batch, head) — the encoder blocks' attention (F.scaled_dot_product_attention in
+ *   models/ulip/pointbert/point_encoder.py's Attention / timm's blocks), kept at fp32-class accuracy.
+ * ua_attn_prepare_f32: qkv [B*N, 3*H*64] (the qkv Linear's output, columns ordered (q|k|v, head, d)) -> (hi, lo) pairs
+ *   Q, K [B*H, N, 64] (Q pre-scaled by log2(e)/8: base-2 softmax) and V^T [B*H, 64, Npad], Npad = ua_attn_padded_tokens(N) (zero padded).
+ * ua_attention_f32: -> (out_hi, out_lo) [B*N, H*64], the A operand of the projection GEMM.
+ * ---------------------------------------------------------------------------------------- */
+long long ua_attn_padded_tokens(int N);
+int ua_attn_prepare_f32(const float* qkv, int B, int N, int H, float* q_hi, float* q_lo, float* k_hi, float* k_lo,
+                        float* vt_hi, float* vt_lo, void* stream);
+int ua_attention_f32(const float* q_hi, const float* q_lo, const float* k_hi, const float* k_lo, const float* vt_hi,
+                     const float* vt_lo, int B, int N, int H, float* out_hi, float* out_lo, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * DOTA (full covariance)
  * Replaces: dota.py:41-63 (fit), :72-87 (predict). dota.py:66-69 (update: DxD inverse) stays a library call.
  *   fit:  mu [K,D], c [K], Sigma [K,D,D], overall [D,D] updated in place from x [B,D], y [B,K].

@@ -170,3 +170,18 @@ def test_tensor_core_head_vs_reference_golden(cuda_device):
     np.testing.assert_allclose(logits.cpu().numpy(), gold["logits"], rtol=1e-4, atol=5e-5)
     np.testing.assert_allclose(prob.cpu().numpy(), gold["prob"], rtol=2e-4, atol=1e-7)
     np.testing.assert_array_equal(arg.cpu().numpy(), gold["pred"])
+
+
+@pytest.mark.parametrize("shape", [(1, 128, 1), (2, 130, 2), (3, 513, 6), (2, 700, 4)])
+def test_tensor_core_attention_vs_sdpa_float64(shape, cuda_device):
+    """csrc/attention.cu (3xTF32, P in tensor memory, base-2 online softmax) vs torch SDPA evaluated in float64."""
+    import torch.nn.functional as F
+    from uniadapter_b200.gemm import attention_tf32x3
+    B, N, H = shape
+    C = H * 64
+    qkv = torch.randn(B * N, 3 * C, generator=torch.Generator().manual_seed(N)).to(cuda_device)
+    hi, lo = attention_tf32x3(qkv, B, N, H)
+    assert int((hi.view(torch.int32) & 0x1fff).abs().max()) == 0
+    q, k, v = qkv.view(B, N, 3, H, 64).permute(2, 0, 3, 1, 4)
+    ref = F.scaled_dot_product_attention(q.double(), k.double(), v.double()).transpose(1, 2).reshape(B * N, C)
+    np.testing.assert_allclose((hi + lo).cpu().numpy(), ref.float().cpu().numpy(), rtol=2e-5, atol=1e-5)

@@ -49,6 +49,9 @@ SIGNATURES = {
     "ua_gemm_tf32x3_f32": (_I, [_P, _P, C.c_longlong, _P, _P, C.c_longlong, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P,
                                  C.c_longlong, _P, _P, _P, _P]),
     "ua_layernorm_split_f32": (_I, [_P, _P, _P, _P, _F, C.c_longlong, _I, _P, _P, _P, _P]),
+    "ua_attn_padded_tokens": (C.c_longlong, [_I]),
+    "ua_attn_prepare_f32": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "ua_attention_f32": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "ua_dota_fit_f32": (_I, [_P, _P, _I, _P, _P, _P, _P, _I, _I, _P]),
     "ua_dota_predict_f16": (_I, [_P, _I, _P, _P, _I, _I, _P, _P]),
     "ua_dota_regularize_f32": (_I, [_P, _I, _F, _P, _P]),

@@ -1,0 +1,471 @@
+// fp32-accurate multi-head self-attention on tcgen05 (3xTF32) for sm_100a: O = softmax(Q K^T / sqrt(d)) V, head dim 64.
+//
+// The transformer blocks of the point encoder are not part of the adaptation path proper, but after the group encoder
+// and the Linear layers moved to the tensor cores, the fp32 SIMT attention torch dispatches (fmha_cutlassF, 182 us per
+// layer at 15 x 6 heads x 513 tokens) was a third of the encoder. This kernel keeps fp32-class accuracy with the same
+// (hi, lo) operand split as gemm_tf32x3.cu.
+//
+//   ua_attn_prepare_f32   qkv [B*N, 3*H*64] fp32 -> Q, K as (hi, lo) [B*H, N, 64] (Q pre-scaled by log2(e)/8) and V^T as
+//                         (hi, lo) [B*H, 64, Npad] (kv contiguous, zero padded to a multiple of 32)
+//   ua_attention_f32      one CTA per (128 query rows, batch*head); kv blocks of 128:
+//       warp 0    TMA producer: Q tile once, then K_j (B operand of S = Q K^T) and V^T_j (B operand of O += P V)
+//       warp 1    TMEM allocation + one lane issuing tcgen05.mma: S_j = Q K_j^T (A, B from smem) and, once the softmax
+//                 warps have published P_j, O += P_j V_j with the A operand read from TENSOR MEMORY (P never touches smem)
+//       warps 2-5 one query row per thread: tcgen05.ld of S_j, online softmax in base 2 (running max / sum, one MUFU.EX2 per weight), rescale of
+//                 the O accumulator in TMEM, tcgen05.st of P_j as a (hi, lo) tf32 pair; at the end O / l as the (hi, lo)
+//                 pair the projection GEMM consumes
+//   TMEM columns: S 128 | P_hi 128 | P_lo 128 | O 64.
+#include <cuda.h>
+#include <string.h>
+#include "common.cuh"
+
+namespace ua {
+namespace {
+
+constexpr int kHd = 64;          // head dimension
+constexpr int kQ = 128;          // query rows per CTA (UMMA M)
+constexpr int kKv = 128;         // kv rows per block
+constexpr int kAttnThreads = 192;
+// 1/sqrt(64) * log2(e): the scores leave the tensor core in base-2 units, so the softmax needs one MUFU.EX2 per weight
+constexpr float kQScale = 0.125f * 1.4426950408889634f;
+
+// ---- PTX wrappers (same conventions as gemm_tf32x3.cu) ----------------------------------------------------------
+__device__ __forceinline__ uint32_t a_elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .b32 rx;\n"
+      ".reg .pred px;\n"
+      "elect.sync rx|px, %1;\n"
+      "@px mov.s32 %0, 1;\n"
+      "}\n"
+      : "+r"(pred)
+      : "r"(0xFFFFFFFFu));
+  return pred;
+}
+__device__ __forceinline__ void a_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void a_tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void a_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void a_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void a_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T
+__device__ __forceinline__ void a_umma_ss(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d),
+      "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem]^T   (A: lane = row, 8 consecutive 32-bit columns = the K slice)
+__device__ __forceinline__ void a_umma_ts(uint32_t d, uint32_t a_tmem, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d),
+      "r"(a_tmem), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void a_tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void a_tmem_st32(uint32_t taddr, const float (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+      "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+      "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+      "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+      "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+      : "memory");
+}
+__device__ __forceinline__ void a_tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint64_t a_smem_desc(uint32_t smem_addr) {   // K-major, 128-byte rows, 128B swizzle
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ uint32_t a_idesc(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// 2^x for x <= 0 (MUFU.EX2, 2 ulp; results below 2^-126 flush to zero, which a softmax weight may do)
+__device__ __forceinline__ float a_exp2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float a_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// ---- operand preparation -----------------------------------------------------------------------------------------
+// grid (ceil(Npad/32), B*H), block 256: a 32-token slab of one head. Q (scaled), K: straight (hi, lo) copies;
+// V: transposed through shared memory so that kv becomes the contiguous dimension.
+__global__ void __launch_bounds__(256)
+    attn_prepare_kernel(const float* __restrict__ qkv, int B, int N, int H, int Npad, float* __restrict__ q_hi,
+                        float* __restrict__ q_lo, float* __restrict__ k_hi, float* __restrict__ k_lo,
+                        float* __restrict__ vt_hi, float* __restrict__ vt_lo) {
+  __shared__ float s_v[32][kHd + 1];
+  const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
+  const int n0 = blockIdx.x * 32;
+  const int C3 = 3 * H * kHd;
+  for (int e = threadIdx.x; e < 32 * kHd; e += 256) {
+    const int r = e / kHd, d = e - r * kHd, n = n0 + r;
+    float q = 0.f, k = 0.f, v = 0.f;
+    if (n < N) {
+      const float* row = qkv + ((size_t)b * N + n) * C3 + h * kHd + d;
+      q = __ldg(row) * kQScale, k = __ldg(row + H * kHd), v = __ldg(row + 2 * H * kHd);
+      const size_t o = ((size_t)bh * N + n) * kHd + d;
+      const float qh = a_tf32(q), kh = a_tf32(k);
+      q_hi[o] = qh, q_lo[o] = q - qh, k_hi[o] = kh, k_lo[o] = k - kh;
+    }
+    s_v[r][d] = v;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 32 * kHd; e += 256) {
+    const int d = e / 32, r = e - d * 32;
+    const float v = s_v[r][d];
+    const float vh = a_tf32(v);
+    const size_t o = ((size_t)bh * kHd + d) * Npad + n0 + r;
+    vt_hi[o] = vh, vt_lo[o] = v - vh;
+  }
+}
+
+struct AttnParams {
+  int N, H, BH;
+  float* out_hi;     // [B*N, H*64]
+  float* out_lo;
+};
+
+struct AttnSmem {
+  static constexpr int kTile = kQ * 128;                 // 128 rows x 128 bytes = 16 KB: one k-block of Q or K
+  static constexpr int kQBytes = 4 * kTile;              // 2 k-blocks x (hi, lo)
+  static constexpr int kKBytes = 4 * kTile;
+  static constexpr int kVTile = kHd * 128;               // 64 rows x 128 bytes = 8 KB: 32 kv of V^T
+  static constexpr int kVBytes = 8 * kVTile;             // 4 k-blocks x (hi, lo)
+  static constexpr int kTotal = kQBytes + kKBytes + kVBytes + 1024 + 256;
+};
+
+__global__ void __launch_bounds__(kAttnThreads, 1)
+    attention_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
+                     const __grid_constant__ CUtensorMap map_k_hi, const __grid_constant__ CUtensorMap map_k_lo,
+                     const __grid_constant__ CUtensorMap map_v_hi, const __grid_constant__ CUtensorMap map_v_lo,
+                     const AttnParams p) {
+  using L = AttnSmem;
+  extern __shared__ unsigned char s_raw[];
+  unsigned char* s_q = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(s_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* s_k = s_q + L::kQBytes;
+  unsigned char* s_v = s_k + L::kKBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_v + L::kVBytes);
+  uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = bars + 2, *v_full = bars + 3, *v_empty = bars + 4,
+           *s_full = bars + 5, *s_free = bars + 6, *p_ready = bars + 7, *o_done = bars + 8;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.y, q0 = blockIdx.x * kQ;
+  const int nkv = (p.N + kKv - 1) / kKv;
+
+  if (warp == 0 && a_elect_one()) {
+    mbar_init(q_full, 1), mbar_init(k_full, 1), mbar_init(k_empty, 1), mbar_init(v_full, 1), mbar_init(v_empty, 1);
+    mbar_init(s_full, 1), mbar_init(s_free, 4), mbar_init(p_ready, 4), mbar_init(o_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  a_fence_before();
+  __syncthreads();
+  a_fence_after();
+  const uint32_t tmem = *s_tmem;
+  const uint32_t t_s = tmem, t_phi = tmem + 128, t_plo = tmem + 256, t_o = tmem + 384;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (a_elect_one()) {
+      const int qrow = bh * p.N + q0;
+      mbar_expect_tx(q_full, (uint32_t)L::kQBytes);
+      for (int kb = 0; kb < 2; ++kb) {
+        a_tma_load_2d(s_q + (2 * kb) * L::kTile, &map_q_hi, q_full, kb * 32, qrow);
+        a_tma_load_2d(s_q + (2 * kb + 1) * L::kTile, &map_q_lo, q_full, kb * 32, qrow);
+      }
+      for (int j = 0; j < nkv; ++j) {
+        const uint32_t ph = (uint32_t)j & 1u;
+        mbar_wait(k_empty, ph ^ 1u);
+        mbar_expect_tx(k_full, (uint32_t)L::kKBytes);
+        const int krow = bh * p.N + j * kKv;
+        for (int kb = 0; kb < 2; ++kb) {
+          a_tma_load_2d(s_k + (2 * kb) * L::kTile, &map_k_hi, k_full, kb * 32, krow);
+          a_tma_load_2d(s_k + (2 * kb + 1) * L::kTile, &map_k_lo, k_full, kb * 32, krow);
+        }
+        mbar_wait(v_empty, ph ^ 1u);
+        mbar_expect_tx(v_full, (uint32_t)L::kVBytes);
+        for (int kb = 0; kb < 4; ++kb) {
+          a_tma_load_2d(s_v + (2 * kb) * L::kVTile, &map_v_hi, v_full, j * kKv + kb * 32, bh * kHd);
+          a_tma_load_2d(s_v + (2 * kb + 1) * L::kVTile, &map_v_lo, v_full, j * kKv + kb * 32, bh * kHd);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (a_elect_one()) {
+      const uint32_t id_s = a_idesc(kQ, kKv), id_o = a_idesc(kQ, kHd);
+      const uint32_t q_base = smem_u32(s_q), k_base = smem_u32(s_k), v_base = smem_u32(s_v);
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < nkv; ++j) {
+        const uint32_t ph = (uint32_t)j & 1u;
+        mbar_wait(k_full, ph);
+        if (j > 0) mbar_wait(s_free, ph ^ 1u);       // the softmax warps have read S_{j-1}
+        a_fence_after();
+        // S_j = Q K_j^T: 2 k-blocks x 4 k-steps x 3 products
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+          const uint64_t qh = a_smem_desc(q_base + (2 * kb) * L::kTile), ql = a_smem_desc(q_base + (2 * kb + 1) * L::kTile);
+          const uint64_t kh = a_smem_desc(k_base + (2 * kb) * L::kTile), kl = a_smem_desc(k_base + (2 * kb + 1) * L::kTile);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t off = (uint64_t)(ks * 2);
+            a_umma_ss(t_s, ql + off, kh + off, id_s, (kb | ks) != 0);
+            a_umma_ss(t_s, qh + off, kl + off, id_s, 1u);
+            a_umma_ss(t_s, qh + off, kh + off, id_s, 1u);
+          }
+        }
+        a_commit(k_empty);
+        a_commit(s_full);
+        // O += P_j V_j once P_j is in tensor memory: 4 k-blocks x 4 k-steps x 3 products, A from TMEM
+        mbar_wait(v_full, ph);
+        mbar_wait(p_ready, ph);
+        a_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+          const uint64_t vh = a_smem_desc(v_base + (2 * kb) * L::kVTile), vl = a_smem_desc(v_base + (2 * kb + 1) * L::kVTile);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t off = (uint64_t)(ks * 2);
+            const uint32_t col = (uint32_t)(kb * 32 + ks * 8);
+            a_umma_ts(t_o, t_plo + col, vh + off, id_o, (uint32_t)((j | kb | ks) != 0));
+            a_umma_ts(t_o, t_phi + col, vl + off, id_o, 1u);
+            a_umma_ts(t_o, t_phi + col, vh + off, id_o, 1u);
+          }
+        }
+        a_commit(v_empty);
+        a_commit(o_done);
+      }
+    }
+  } else {
+    // ===== softmax / epilogue warps: one query row per thread =====
+    const int quarter = warp & 3;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const int qi = q0 + quarter * 32 + lane;           // token index of this row
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < nkv; ++j) {
+      const uint32_t ph = (uint32_t)j & 1u;
+      const int kv_valid = min(kKv, p.N - j * kKv);    // columns beyond the sequence are masked
+      mbar_wait(s_full, ph);
+      a_fence_after();
+      // pass 1: row maximum of the block (columns beyond the sequence count as -inf; branch-free so that the 32
+      // per-column chains of a thread interleave)
+      float bmax = -INFINITY;
+#pragma unroll 1
+      for (int c0 = 0; c0 < kKv; c0 += 32) {
+        if (c0 >= kv_valid) break;
+        float v[32];
+        a_tmem_ld32(t_s + lane_off + (uint32_t)c0, v);
+        const int nv = kv_valid - c0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) bmax = fmaxf(bmax, i < nv ? v[i] : -INFINITY);
+      }
+      const float m_new = fmaxf(m_run, bmax);
+      const float alpha = a_exp2(m_run - m_new);       // 0 at the first block (m_run = -inf)
+      // the previous PV must have finished before O is rescaled and before P is overwritten
+      if (j > 0) {
+        mbar_wait(o_done, ph ^ 1u);
+        a_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < kHd; c0 += 32) {
+          float o[32];
+          a_tmem_ld32(t_o + lane_off + (uint32_t)c0, o);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] *= alpha;
+          a_tmem_st32(t_o + lane_off + (uint32_t)c0, o);
+        }
+      }
+      // pass 2: P = 2^(S - m_new) as a (hi, lo) pair into tensor memory, running sum
+      float psum = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < kKv; c0 += 32) {
+        float v[32], hi[32];
+        if (c0 < kv_valid) {
+          a_tmem_ld32(t_s + lane_off + (uint32_t)c0, v);
+          const int nv = kv_valid - c0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float e = a_exp2((i < nv ? v[i] : -INFINITY) - m_new);
+            psum += e;
+            hi[i] = a_tf32(e);
+            v[i] = e - hi[i];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) hi[i] = 0.f, v[i] = 0.f;
+        }
+        a_tmem_st32(t_phi + lane_off + (uint32_t)c0, hi);
+        a_tmem_st32(t_plo + lane_off + (uint32_t)c0, v);
+      }
+      a_tmem_st_wait();
+      l_run = l_run * alpha + psum;
+      m_run = m_new;
+      a_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        a_mbar_arrive(s_free);      // S_j has been consumed
+        a_mbar_arrive(p_ready);     // P_j (and the rescaled O) are in tensor memory
+      }
+    }
+    // epilogue: O / l as the (hi, lo) pair of the projection GEMM's A operand
+    mbar_wait(o_done, (uint32_t)(nkv - 1) & 1u);
+    a_fence_after();
+    const float inv_l = __fdiv_rn(1.0f, l_run);
+    const int b = bh / p.H, h = bh - b * p.H;
+#pragma unroll 1
+    for (int c0 = 0; c0 < kHd; c0 += 32) {
+      float o[32];
+      a_tmem_ld32(t_o + lane_off + (uint32_t)c0, o);
+      if (qi < p.N) {
+        const size_t off = ((size_t)b * p.N + qi) * (size_t)(p.H * kHd) + h * kHd + c0;
+        float4* oh = reinterpret_cast<float4*>(p.out_hi + off);
+        float4* ol = reinterpret_cast<float4*>(p.out_lo + off);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 hv, lv;
+          float x;
+          x = o[4 * i] * inv_l, hv.x = a_tf32(x), lv.x = x - hv.x;
+          x = o[4 * i + 1] * inv_l, hv.y = a_tf32(x), lv.y = x - hv.y;
+          x = o[4 * i + 2] * inv_l, hv.z = a_tf32(x), lv.z = x - hv.z;
+          x = o[4 * i + 3] * inv_l, hv.w = a_tf32(x), lv.w = x - hv.w;
+          oh[i] = hv, ol[i] = lv;
+        }
+      }
+    }
+  }
+  a_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int attn_map(CUtensorMap* map, const float* base, long long rows, long long cols, int box_rows) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  if (!fn) {
+    set_error("ua_attention_f32: cuTensorMapEncodeTiled is not available from the driver");
+    return UA_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
+  cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("ua_attention_f32: cuTensorMapEncodeTiled failed with %d", (int)r);
+    return UA_ERR_CUDA;
+  }
+  return UA_OK;
+}
+
+}  // namespace
+}  // namespace ua
+
+extern "C" long long ua_attn_padded_tokens(int N) { return ((long long)N + 31) / 32 * 32; }
+
+extern "C" int ua_attn_prepare_f32(const float* qkv, int B, int N, int H, float* q_hi, float* q_lo, float* k_hi,
+                                   float* k_lo, float* vt_hi, float* vt_lo, void* stream) {
+  using namespace ua;
+  UA_REQUIRE(qkv && q_hi && q_lo && k_hi && k_lo && vt_hi && vt_lo, "ua_attn_prepare_f32: NULL pointer");
+  UA_REQUIRE(B >= 1 && N >= 1 && H >= 1 && (long long)B * H <= 65535, "ua_attn_prepare_f32: bad sizes B=%d N=%d H=%d", B,
+             N, H);
+  const int Npad = (int)ua_attn_padded_tokens(N);
+  dim3 grid(Npad / 32, B * H);
+  attn_prepare_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(qkv, B, N, H, Npad, q_hi, q_lo, k_hi, k_lo, vt_hi, vt_lo);
+  return check_launch("ua_attn_prepare_f32");
+}
+
+extern "C" int ua_attention_f32(const float* q_hi, const float* q_lo, const float* k_hi, const float* k_lo,
+                                const float* vt_hi, const float* vt_lo, int B, int N, int H, float* out_hi,
+                                float* out_lo, void* stream) {
+  using namespace ua;
+  UA_REQUIRE(q_hi && q_lo && k_hi && k_lo && vt_hi && vt_lo && out_hi && out_lo, "ua_attention_f32: NULL pointer");
+  UA_REQUIRE(B >= 1 && N >= 1 && H >= 1 && (long long)B * H <= 65535, "ua_attention_f32: bad sizes B=%d N=%d H=%d", B, N, H);
+  UA_REQUIRE((uintptr_t)out_hi % 16 == 0 && (uintptr_t)out_lo % 16 == 0, "ua_attention_f32: outputs must be 16-byte aligned");
+  const int BH = B * H;
+  const long long Npad = ua_attn_padded_tokens(N);
+  CUtensorMap mq_hi, mq_lo, mk_hi, mk_lo, mv_hi, mv_lo;
+  int rc;
+  if ((rc = attn_map(&mq_hi, q_hi, (long long)BH * N, kHd, kQ)) != UA_OK) return rc;
+  if ((rc = attn_map(&mq_lo, q_lo, (long long)BH * N, kHd, kQ)) != UA_OK) return rc;
+  if ((rc = attn_map(&mk_hi, k_hi, (long long)BH * N, kHd, kKv)) != UA_OK) return rc;
+  if ((rc = attn_map(&mk_lo, k_lo, (long long)BH * N, kHd, kKv)) != UA_OK) return rc;
+  if ((rc = attn_map(&mv_hi, vt_hi, (long long)BH * kHd, Npad, kHd)) != UA_OK) return rc;
+  if ((rc = attn_map(&mv_lo, vt_lo, (long long)BH * kHd, Npad, kHd)) != UA_OK) return rc;
+  AttnParams p;
+  p.N = N, p.H = H, p.BH = BH, p.out_hi = out_hi, p.out_lo = out_lo;
+  cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::kTotal);
+  if (e != cudaSuccess) {
+    set_error("ua_attention_f32: cudaFuncSetAttribute(%d B): %s", AttnSmem::kTotal, cudaGetErrorString(e));
+    return UA_ERR_CUDA;
+  }
+  dim3 grid((N + kQ - 1) / kQ, BH);
+  attention_kernel<<<grid, kAttnThreads, AttnSmem::kTotal, (cudaStream_t)stream>>>(mq_hi, mq_lo, mk_hi, mk_lo, mv_hi,
+                                                                                   mv_lo, p);
+  return check_launch("ua_attention_f32");
+}

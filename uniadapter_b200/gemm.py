@@ -154,13 +154,33 @@ class LinearPlan:
         return gemm_tf32x3(a, self.w, bias=self.b, relu=relu, out=True)['out'].reshape(*lead, self.N)
 
 
+def attention_tf32x3(qkv: torch.Tensor, B: int, N: int, H: int):
+    """qkv [B*N, 3*H*64] fp32 (columns ordered q|k|v, head, d) -> (hi, lo) of softmax(q k^T / 8) v, [B*N, H*64]
+    (csrc/attention.cu: tcgen05, P kept in tensor memory)."""
+    dev = qkv.device
+    qkv = qkv.contiguous()
+    npad = int(_lib.lib().ua_attn_padded_tokens(N))
+    e = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+    q_hi, q_lo, k_hi, k_lo = (e(B * H, N, 64) for _ in range(4))
+    vt_hi, vt_lo = e(B * H, 64, npad), e(B * H, 64, npad)
+    rc = _lib.lib().ua_attn_prepare_f32(_lib.ptr(qkv), B, N, H, _lib.ptr(q_hi), _lib.ptr(q_lo), _lib.ptr(k_hi),
+                                       _lib.ptr(k_lo), _lib.ptr(vt_hi), _lib.ptr(vt_lo), _lib.stream_ptr())
+    _lib.check(rc, "ua_attn_prepare_f32")
+    out_hi, out_lo = e(B * N, H * 64), e(B * N, H * 64)
+    rc = _lib.lib().ua_attention_f32(_lib.ptr(q_hi), _lib.ptr(q_lo), _lib.ptr(k_hi), _lib.ptr(k_lo), _lib.ptr(vt_hi),
+                                    _lib.ptr(vt_lo), B, N, H, _lib.ptr(out_hi), _lib.ptr(out_lo), _lib.stream_ptr())
+    _lib.check(rc, "ua_attention_f32")
+    return out_hi, out_lo
+
+
 class BlockPlan:
     """A pre-LN transformer block with every dense layer on the tensor-core GEMM and the element-wise work fused around
     it: (x + pos, LayerNorm, split) in one kernel, the skip connections in the proj / fc2 epilogues, GELU + split in the
-    fc1 epilogue. Attention itself stays torch SDPA (the north star keeps it in PyTorch)."""
+    fc1 epilogue. Attention runs on csrc/attention.cu when the head dimension is 64 (torch SDPA otherwise)."""
 
-    def __init__(self, block):
+    def __init__(self, block, tc_attention=True):
         self.block = block
+        self.tc_attention = tc_attention
         self.qkv, self.proj = LinearPlan(block.attn.qkv), LinearPlan(block.attn.proj)
         self.fc1, self.fc2 = LinearPlan(block.mlp.fc1), LinearPlan(block.mlp.fc2)
 
@@ -178,9 +198,12 @@ class BlockPlan:
         h, xs = layernorm_split(x, blk.norm1, pos, want_sum=True) if pos is not None else (layernorm_split(x, blk.norm1), x)
         flat = lambda pair: (pair[0].view(B * N, -1), pair[1].view(B * N, -1))
         qkv = gemm_tf32x3(flat(h), self.qkv.w, bias=self.qkv.b, out=True)['out']
-        q, k, v = qkv.view(B, N, 3, H, C // H).permute(2, 0, 3, 1, 4)
-        a = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B * N, C)
-        x1 = gemm_tf32x3(split_tf32(a), self.proj.w, bias=self.proj.b, residual=xs.view(B * N, C), out=True)['out']
+        if C // H == 64 and self.tc_attention:
+            a = attention_tf32x3(qkv, B, N, H)               # tcgen05 attention, already the (hi, lo) pair proj needs
+        else:
+            q, k, v = qkv.view(B, N, 3, H, C // H).permute(2, 0, 3, 1, 4)
+            a = split_tf32(F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B * N, C))
+        x1 = gemm_tf32x3(a, self.proj.w, bias=self.proj.b, residual=xs.view(B * N, C), out=True)['out']
         h2 = layernorm_split(x1, blk.norm2)
         g = gemm_tf32x3(h2, self.fc1.w, bias=self.fc1.b, act='gelu', out_split=True)['out_split']
         x2 = gemm_tf32x3(g, self.fc2.w, bias=self.fc2.b, residual=x1, out=True)['out']
