@@ -25,6 +25,13 @@ for (B, N, H) in cases:
     for _ in range(5):
         attention_tf32x3(qkv, B, N, H)
     e.record(); torch.cuda.synchronize(); us = s.elapsed_time(e) / 5 * 1e3
+    from uniadapter_b200 import _lib
+    tl = _lib.enable_kernel_timing(True)
+    for _ in range(5):
+        attention_tf32x3(qkv, B, N, H)
+    torch.cuda.synchronize()
+    print("   ", {k_: round(v_[2], 1) for k_, v_ in tl.summary().items()})
+    _lib.enable_kernel_timing(False)
     s.record()
     for _ in range(5):
         F.scaled_dot_product_attention(q, k, v)

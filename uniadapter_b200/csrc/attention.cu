@@ -137,15 +137,16 @@ __device__ __forceinline__ float a_tf32(float x) {
 }
 
 // ---- operand preparation -----------------------------------------------------------------------------------------
-// grid (ceil(Npad/32), B*H), block 256: a 32-token slab of one head. Q (scaled), K: straight (hi, lo) copies;
+// 1-D grid of B*H*(Npad/32) slabs, block 256: a 32-token slab of one head. Q (scaled), K: straight (hi, lo) copies;
 // V: transposed through shared memory so that kv becomes the contiguous dimension.
 __global__ void __launch_bounds__(256)
     attn_prepare_kernel(const float* __restrict__ qkv, int B, int N, int H, int Npad, float* __restrict__ q_hi,
                         float* __restrict__ q_lo, float* __restrict__ k_hi, float* __restrict__ k_lo,
                         float* __restrict__ vt_hi, float* __restrict__ vt_lo) {
   __shared__ float s_v[32][kHd + 1];
-  const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
-  const int n0 = blockIdx.x * 32;
+  const int nslab = Npad / 32;
+  const int bh = (int)blockIdx.x / nslab, b = bh / H, h = bh - b * H;
+  const int n0 = ((int)blockIdx.x - bh * nslab) * 32;
   const int C3 = 3 * H * kHd;
   for (int e = threadIdx.x; e < 32 * kHd; e += 256) {
     const int r = e / kHd, d = e - r * kHd, n = n0 + r;
@@ -256,7 +257,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
         mbar_wait(k_full, ph);
         if (j > 0) mbar_wait(s_free, ph ^ 1u);       // the softmax warps have read S_{j-1}
         a_fence_after();
-        // S_j = Q K_j^T: 2 k-blocks x 4 k-steps x 3 products
+        // S_j = Q K_j^T: 2 k-blocks x 4 k-steps x 3 products; a short last block only computes the columns it has
+        const int kv_valid = min(kKv, p.N - j * kKv);
+        const uint32_t id_sj = kv_valid == kKv ? id_s : a_idesc(kQ, (kv_valid + 15) & ~15);
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb) {
           const uint64_t qh = a_smem_desc(q_base + (2 * kb) * L::kTile), ql = a_smem_desc(q_base + (2 * kb + 1) * L::kTile);
@@ -264,9 +267,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint64_t off = (uint64_t)(ks * 2);
-            a_umma_ss(t_s, ql + off, kh + off, id_s, (kb | ks) != 0);
-            a_umma_ss(t_s, qh + off, kl + off, id_s, 1u);
-            a_umma_ss(t_s, qh + off, kh + off, id_s, 1u);
+            a_umma_ss(t_s, ql + off, kh + off, id_sj, (kb | ks) != 0);
+            a_umma_ss(t_s, qh + off, kl + off, id_sj, 1u);
+            a_umma_ss(t_s, qh + off, kh + off, id_sj, 1u);
           }
         }
         a_commit(k_empty);
@@ -275,16 +278,19 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
         mbar_wait(v_full, ph);
         mbar_wait(p_ready, ph);
         a_fence_after();
+        const int ksteps = (kv_valid + 7) >> 3;      // 8 kv per MMA; a short last block stops early
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb) {
           const uint64_t vh = a_smem_desc(v_base + (2 * kb) * L::kVTile), vl = a_smem_desc(v_base + (2 * kb + 1) * L::kVTile);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t off = (uint64_t)(ks * 2);
-            const uint32_t col = (uint32_t)(kb * 32 + ks * 8);
-            a_umma_ts(t_o, t_plo + col, vh + off, id_o, (uint32_t)((j | kb | ks) != 0));
-            a_umma_ts(t_o, t_phi + col, vl + off, id_o, 1u);
-            a_umma_ts(t_o, t_phi + col, vh + off, id_o, 1u);
+            if (kb * 4 + ks < ksteps) {
+              const uint64_t off = (uint64_t)(ks * 2);
+              const uint32_t col = (uint32_t)(kb * 32 + ks * 8);
+              a_umma_ts(t_o, t_plo + col, vh + off, id_o, (uint32_t)((j | kb | ks) != 0));
+              a_umma_ts(t_o, t_phi + col, vl + off, id_o, 1u);
+              a_umma_ts(t_o, t_phi + col, vh + off, id_o, 1u);
+            }
           }
         }
         a_commit(v_empty);
@@ -333,6 +339,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
       float psum = 0.f;
 #pragma unroll 1
       for (int c0 = 0; c0 < kKv; c0 += 32) {
+        if (c0 >= kv_valid) break;                     // the PV MMAs stop at ceil(kv_valid / 8) * 8 columns
         float v[32], hi[32];
         if (c0 < kv_valid) {
           a_tmem_ld32(t_s + lane_off + (uint32_t)c0, v);
@@ -435,7 +442,7 @@ extern "C" int ua_attn_prepare_f32(const float* qkv, int B, int N, int H, float*
   UA_REQUIRE(B >= 1 && N >= 1 && H >= 1 && (long long)B * H <= 65535, "ua_attn_prepare_f32: bad sizes B=%d N=%d H=%d", B,
              N, H);
   const int Npad = (int)ua_attn_padded_tokens(N);
-  dim3 grid(Npad / 32, B * H);
+  const unsigned grid = (unsigned)((long long)B * H * (Npad / 32));
   attn_prepare_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(qkv, B, N, H, Npad, q_hi, q_lo, k_hi, k_lo, vt_hi, vt_lo);
   return check_launch("ua_attn_prepare_f32");
 }
@@ -464,7 +471,10 @@ extern "C" int ua_attention_f32(const float* q_hi, const float* q_lo, const floa
     set_error("ua_attention_f32: cudaFuncSetAttribute(%d B): %s", AttnSmem::kTotal, cudaGetErrorString(e));
     return UA_ERR_CUDA;
   }
-  dim3 grid((N + kQ - 1) / kQ, BH);
+  // One CTA per 128 query rows. (Handing the one leftover row of 512 + 1 tokens to a SIMT side kernel, so that every
+  // (batch, head) needs 4 CTAs instead of 5, was tried: the latency-bound side kernel cost what the saved wave gained.)
+  const int q_tiles = (N + kQ - 1) / kQ;
+  dim3 grid(q_tiles, BH);
   attention_kernel<<<grid, kAttnThreads, AttnSmem::kTotal, (cudaStream_t)stream>>>(mq_hi, mq_lo, mk_hi, mk_lo, mv_hi,
                                                                                    mv_lo, p);
   return check_launch("ua_attention_f32");

@@ -163,10 +163,10 @@ def attention_tf32x3(qkv: torch.Tensor, B: int, N: int, H: int):
     e = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
     q_hi, q_lo, k_hi, k_lo = (e(B * H, N, 64) for _ in range(4))
     vt_hi, vt_lo = e(B * H, 64, npad), e(B * H, 64, npad)
+    out_hi, out_lo = e(B * N, H * 64), e(B * N, H * 64)
     rc = _lib.lib().ua_attn_prepare_f32(_lib.ptr(qkv), B, N, H, _lib.ptr(q_hi), _lib.ptr(q_lo), _lib.ptr(k_hi),
                                        _lib.ptr(k_lo), _lib.ptr(vt_hi), _lib.ptr(vt_lo), _lib.stream_ptr())
     _lib.check(rc, "ua_attn_prepare_f32")
-    out_hi, out_lo = e(B * N, H * 64), e(B * N, H * 64)
     rc = _lib.lib().ua_attention_f32(_lib.ptr(q_hi), _lib.ptr(q_lo), _lib.ptr(k_hi), _lib.ptr(k_lo), _lib.ptr(vt_hi),
                                     _lib.ptr(vt_lo), B, N, H, _lib.ptr(out_hi), _lib.ptr(out_lo), _lib.stream_ptr())
     _lib.check(rc, "ua_attention_f32")
