@@ -33,7 +33,7 @@ N_POINTS, N_CLASSES, FEAT_DIM, MODES = 1024, 40, 512, 8
 # dram__bytes_read.sum + dram__bytes_write.sum of one LVIS-scale launch (ncu --set full, profiles/r1_modedota_lvis.txt):
 # 75.9 MB read + 17.2 MB written inside the kernel; the rest of the 75.8 MB of output is still dirty in L2 at exit.
 LVIS_DRAM_TRAFFIC_BYTES = 93_060_000
-GEMM_DRAM_TRAFFIC_BYTES = None    # filled from the ncu --set full capture of the dominant GEMM launch (profiles/)
+GEMM_DRAM_TRAFFIC_BYTES = 1_468_000_000   # largest GEMM launch of the step (group-encoder conv3: 245 760 x 512 x 256, split output): 520.7 MB read + 947.3 MB written (ncu --set full, profiles/r1_ncu_hot_kernels.txt)
 WORKLOAD = "ULIP-2 PointBERT (random init) + MODE-DOTA M=8 + res-learning, synthetic ModelNet40-C streams, 1024 pts, 40 classes, batch 1/stream"
 
 
