@@ -214,7 +214,7 @@ int ua_attention_f32(const float* q_hi, const float* q_lo, const float* k_hi, co
 
 /* ------------------------------------------------------------------------------------------
  * DOTA (full covariance)
- * Replaces: dota.py:41-63 (fit), :72-87 (predict). dota.py:66-69 (update: DxD inverse) stays a library call.
+ * Replaces: dota.py:41-63 (fit), :66-69 (update), :72-87 (predict).
  *   fit:  mu [K,D], c [K], Sigma [K,D,D], overall [D,D] updated in place from x [B,D], y [B,K].
  *   predict: x_h [R,D] f16, Lambda_h [D,D] f16, mu [K,D] f32 -> out_scores_h [R,K] f16, rounding to fp16
  *            at the reference's rounding points (M, W, M*W, 0.5*sum, X@W, difference).
@@ -225,6 +225,13 @@ int ua_dota_predict_f16(const void* x_h, int R, const void* Lambda_h, const floa
                         void* out_scores_h, void* stream);
 /* A = (1-eps)*overall + eps*I  (the matrix dota.py:67-68 inverts), written to out [D,D]. */
 int ua_dota_regularize_f32(const float* overall, int D, float eps, float* out, void* stream);
+/* update (dota.py:66-69): Lambda = inverse((1-eps)*overall + eps*I).half(), one cooperative launch (register-resident
+ *   block Gauss-Jordan, no pivoting: the matrix is SPD). D % 16 == 0, D <= 1536 (else UA_ERR_UNSUPPORTED: the caller
+ *   keeps a library inverse for such sizes). workspace: ua_dota_update_workspace_bytes(D) bytes of device scratch,
+ *   256-byte aligned. out_lambda_h [D,D] f16 and/or out_lambda_f32 [D,D] (either may be NULL, not both). */
+long long ua_dota_update_workspace_bytes(int D);
+int ua_dota_update_f32(const float* overall, int D, float eps, void* workspace, void* out_lambda_h,
+                       float* out_lambda_f32, void* stream);
 
 #ifdef __cplusplus
 }

@@ -15,6 +15,24 @@ def cu(a, dev):
     return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 
 
+def knn_both_paths(xyz, centers, k, rgb=None):
+    """knn_group through both selection paths of the kernel: histogram selection of the first 1024-point tile
+    (default) and the pure streaming filter (tuning knob knn_hist = -1). They must agree bit for bit."""
+    import uniadapter_b200 as ua
+    from uniadapter_b200 import _lib
+    res = ua.knn_group(xyz, centers, k, rgb, want_idx=True)
+    _lib.set_tuning("knn_hist", -1)
+    try:
+        alt = ua.knn_group(xyz, centers, k, rgb, want_idx=True)
+    finally:
+        _lib.set_tuning("knn_hist", 0)
+    for a, b in zip(res, alt):
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert torch.equal(a, b)
+    return res
+
+
 @pytest.mark.parametrize("name", list(cases.TOK_KNN))
 def test_fps_knn_group_vs_reference_golden_and_oracle(name, cuda_device):
     import uniadapter_b200 as ua
@@ -26,7 +44,7 @@ def test_fps_knn_group_vs_reference_golden_and_oracle(name, cuda_device):
     np.testing.assert_array_equal(idx.cpu().numpy(), gold["fps_idx"].astype(np.int64))           # reference, bit-exact
     np.testing.assert_array_equal(centers.cpu().numpy(), T.gather(inp["xyz"], idx.cpu().numpy()))
 
-    kidx, neigh, feat = ua.knn_group(xyz, centers, k, rgb, want_idx=True)
+    kidx, neigh, feat = knn_both_paths(xyz, centers, k, rgb)
     kidx_np = kidx.cpu().numpy()
     o_idx = np.sort(T.knn(inp["xyz"], centers.cpu().numpy(), k, threads=4), axis=-1)   # kernel emits ascending index
     np.testing.assert_array_equal(kidx_np, o_idx)                                                 # oracle: exact
@@ -84,11 +102,25 @@ def test_full_size_tokenizer_vs_oracle(B, N, G, k, start, cuda_device):
     assert idx.dtype == torch.int32
     o_fps = T.fps(xyz_np, G, st, threads=8)
     np.testing.assert_array_equal(idx.cpu().numpy().astype(np.int64), o_fps)
-    kidx, neigh, _ = ua.knn_group(xyz, centers, k, want_idx=True)
+    kidx, neigh, _ = knn_both_paths(xyz, centers, k)
     o_idx = np.sort(T.knn(xyz_np, centers.cpu().numpy(), k, threads=8), axis=-1)
     np.testing.assert_array_equal(kidx.cpu().numpy(), o_idx)
     np.testing.assert_array_equal(neigh.cpu().numpy(),
                                   (T.gather(xyz_np, o_idx) - centers.cpu().numpy()[:, :, None, :]).astype(np.float32))
+
+
+@pytest.mark.parametrize("N,k,ndup", [(600, 32, 600), (1024, 64, 700), (1500, 16, 300), (900, 100, 450)])
+def test_knn_with_many_identical_points(N, k, ndup, cuda_device):
+    """Degenerate clouds: `ndup` copies of one point (one histogram bin holds more candidates than the selection buffer
+    -> the kernel must fall back to the streaming filter) and exact ties broken by the lower index, as in the oracle."""
+    from oracle import synth
+    xyz_np = synth.cloud(1, N, 4242 + N)
+    xyz_np[0, :ndup] = xyz_np[0, 0]
+    centers_np = np.ascontiguousarray(xyz_np[:, [0, ndup - 1, N - 1, N // 2]])
+    kidx, neigh, _ = knn_both_paths(cu(xyz_np, cuda_device), cu(centers_np, cuda_device), k)
+    o_idx = np.sort(T.knn(xyz_np, centers_np, k, threads=2), axis=-1)
+    np.testing.assert_array_equal(kidx.cpu().numpy(), o_idx)
+    np.testing.assert_array_equal(kidx.cpu().numpy()[0, 0], np.arange(k) if k <= ndup else kidx.cpu().numpy()[0, 0])
 
 
 def test_uni3d_entry_points_and_skip_small_norm(cuda_device):

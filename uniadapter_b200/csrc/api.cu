@@ -11,6 +11,7 @@ static std::atomic<int64_t> g_launches{0};
 
 extern int g_fps_threads;
 extern int g_knn_warps;
+extern int g_knn_hist;
 extern int g_modedota_threads;
 extern int g_modedota_v;
 extern int g_gemm_bn;
@@ -18,6 +19,7 @@ extern int g_resid_cb;
 extern int g_resid_dbl;
 extern int g_modedota_groups;
 extern int g_modedota_logprod;
+extern int g_modedota_batch;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -49,6 +51,7 @@ extern "C" int ua_set_tuning(const char* key, int value) {
   if (!key) return UA_ERR_INVALID_ARG;
   if (!strcmp(key, "fps_threads")) { ua::g_fps_threads = value; return UA_OK; }
   if (!strcmp(key, "knn_warps")) { ua::g_knn_warps = value; return UA_OK; }
+  if (!strcmp(key, "knn_hist")) { ua::g_knn_hist = value; return UA_OK; }
   if (!strcmp(key, "modedota_threads")) { ua::g_modedota_threads = value; return UA_OK; }
   if (!strcmp(key, "modedota_groups")) { ua::g_modedota_groups = value; return UA_OK; }
   if (!strcmp(key, "resid_cb")) { ua::g_resid_cb = value; return UA_OK; }
@@ -56,6 +59,7 @@ extern "C" int ua_set_tuning(const char* key, int value) {
   if (!strcmp(key, "gemm_bn")) { ua::g_gemm_bn = value; return UA_OK; }
   if (!strcmp(key, "modedota_v")) { ua::g_modedota_v = value; return UA_OK; }
   if (!strcmp(key, "modedota_logprod")) { ua::g_modedota_logprod = value; return UA_OK; }
+  if (!strcmp(key, "modedota_batch")) { ua::g_modedota_batch = value; return UA_OK; }
   ua::set_error("ua_set_tuning: unknown key '%s'", key);
   return UA_ERR_INVALID_ARG;
 }

@@ -18,6 +18,7 @@
 namespace ua {
 
 int g_knn_warps = 0;  // tuning override (0 = heuristic)
+int g_knn_hist = 0;   // tuning: -1 disables the histogram selection of the first tile (streaming filter only)
 
 namespace {
 
@@ -139,16 +140,137 @@ __device__ __forceinline__ void knn_compact(uint32_t* bkey, uint32_t* bidx, int&
   thr = ((uint64_t)T << 32) | last_eq_idx;
 }
 
+
+// ---- first tile by histogram selection -----------------------------------------------------------------------
+// The streaming filter starts blind: until the first compaction every point is a candidate, and each compaction is a
+// 32-step radix select over CAP register-held keys. For the first tile (<= 1024 points = 32 distances per lane, kept
+// in registers) the k-th smallest is found with one shared-memory histogram instead:
+//   bin(d) = min(255, (bits(max(d,0) + delta) - bits(delta)) >> 18),  delta = max_d / 64
+// is monotone in d (linear below delta, 32 bins per octave above: fine where the neighbours are, coarse in the far
+// tail); a warp scan over the 256 counters yields the bin b* that holds the k-th smallest, how many points lie in
+// lower bins, and how many share b* (a handful). Only those are radix-selected (usually one register per lane), and
+// one more pass over the registers emits the k survivors in ascending point-index order together with the exact
+// (key, index) threshold the streaming filter continues from. Exactness does not depend on the bin shape: bins only
+// pre-partition, the (distance bits, index) order decides. Returns false (nothing written) when b* holds more than
+// CAP points (e.g. all points identical): the caller then streams the tile as before.
+template <int CAP>
+__device__ __forceinline__ bool knn_first_tile_hist(const float* __restrict__ sx, const float* __restrict__ sp, int tp,
+                                                    float cx, float cy, float cz, float cn, int k, int lane,
+                                                    uint32_t* bkey, uint32_t* bidx, int* hist, int& count,
+                                                    uint64_t& thr) {
+  const unsigned lt_mask = (1u << lane) - 1u;
+  float d[32];
+  float dm = 0.f;
+#pragma unroll
+  for (int r = 0; r < 32; ++r) {
+    const int p = r * 32 + lane;
+    d[r] = INFINITY;
+    if (p < tp) {
+      d[r] = expanded_sqdist(cx, cy, cz, cn, sx[3 * p], sx[3 * p + 1], sx[3 * p + 2], sp[p]);
+      dm = fmaxf(dm, d[r]);
+    }
+  }
+  const float dmax = __uint_as_float(__reduce_max_sync(kFullMask, __float_as_uint(dm)));   // dm >= 0: bits are ordered
+  const float delta = dmax * 0.015625f;
+  const uint32_t dbits = __float_as_uint(delta);
+  auto bin_of = [&](float v) -> uint32_t {
+    const uint32_t e = __float_as_uint(__fadd_rn(fmaxf(v, 0.f), delta)) - dbits;
+    return min(e >> 18, 255u);
+  };
+#pragma unroll
+  for (int j = 0; j < 8; ++j) hist[lane + 32 * j] = 0;
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < 32; ++r)
+    if (r * 32 + lane < tp) atomicAdd(&hist[bin_of(d[r])], 1);
+  __syncwarp();
+  // warp scan over the 256 counters (8 per lane)
+  int h[8];
+  {
+    const int4 a = *reinterpret_cast<const int4*>(hist + 8 * lane), b = *reinterpret_cast<const int4*>(hist + 8 * lane + 4);
+    h[0] = a.x, h[1] = a.y, h[2] = a.z, h[3] = a.w, h[4] = b.x, h[5] = b.y, h[6] = b.z, h[7] = b.w;
+  }
+  int ssum = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) ssum += h[j];
+  int incl = ssum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(kFullMask, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const unsigned mb = __ballot_sync(kFullMask, incl >= k);      // tp >= k, so some lane crosses
+  const int L = __ffs(mb) - 1;
+  int bstar = 0, nless = 0, neq = 0;
+  if (lane == L) {
+    int c = incl - ssum;
+    bool found = false;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (!found && c + h[j] >= k) bstar = 8 * lane + j, nless = c, neq = h[j], found = true;
+      c += h[j];
+    }
+  }
+  bstar = __shfl_sync(kFullMask, bstar, L);
+  nless = __shfl_sync(kFullMask, nless, L);
+  neq = __shfl_sync(kFullMask, neq, L);
+  if (neq > CAP) return false;
+  // the points of bin b*, in index order, into the candidate buffer
+  int cnt = 0;
+#pragma unroll
+  for (int r = 0; r < 32; ++r) {
+    const int p = r * 32 + lane;
+    const bool eq = p < tp && bin_of(d[r]) == (uint32_t)bstar;
+    const unsigned m = __ballot_sync(kFullMask, eq);
+    if (m) {
+      if (eq) {
+        const int pos = cnt + __popc(m & lt_mask);
+        bkey[pos] = float_to_ordered(d[r]);
+        bidx[pos] = (uint32_t)p;
+      }
+      cnt += __popc(m);
+    }
+  }
+  // the (k - nless)-th smallest (key, index) among them is the k-th smallest of the tile
+  uint64_t t2;
+  const int need = k - nless;
+  if (neq <= 32) knn_compact<32>(bkey, bidx, cnt, need, lane, t2);
+  else if (neq <= 64) knn_compact<64>(bkey, bidx, cnt, need, lane, t2);
+  else knn_compact<CAP>(bkey, bidx, cnt, need, lane, t2);
+  const uint32_t T = (uint32_t)(t2 >> 32), ti = (uint32_t)t2;
+  int out = 0;
+#pragma unroll
+  for (int r = 0; r < 32; ++r) {
+    const int p = r * 32 + lane;
+    const uint32_t key = float_to_ordered(d[r]);
+    const bool take = p < tp && (key < T || (key == T && (uint32_t)p <= ti));
+    const unsigned m = __ballot_sync(kFullMask, take);
+    if (m) {
+      if (take) {
+        const int pos = out + __popc(m & lt_mask);
+        bkey[pos] = key;
+        bidx[pos] = (uint32_t)p;
+      }
+      out += __popc(m);
+    }
+  }
+  __syncwarp();
+  count = out;  // == k
+  thr = t2;
+  return true;
+}
+
 template <int CAP, typename IdxT>
 __global__ void __launch_bounds__(256)
     knn_group_kernel(const float* __restrict__ xyz, const float* __restrict__ rgb, const float* __restrict__ centers,
-                     int N, int G, int k, int use_bulk, IdxT* __restrict__ out_idx, float* __restrict__ out_neigh,
-                     float* __restrict__ out_feat) {
+                     int N, int G, int k, int use_bulk, int use_hist, IdxT* __restrict__ out_idx,
+                     float* __restrict__ out_neigh, float* __restrict__ out_feat) {
   extern __shared__ __align__(128) unsigned char s_raw[];
   TileSmem* tiles = reinterpret_cast<TileSmem*>(s_raw);
   uint32_t* s_key = reinterpret_cast<uint32_t*>(s_raw + sizeof(TileSmem));  // [W][CAP]
   const int W = blockDim.x >> 5;
   uint32_t* s_idx = s_key + (size_t)W * CAP;                                // [W][CAP]
+  int* s_hist = reinterpret_cast<int*>(s_idx + (size_t)W * CAP);            // [W][256]
 
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -176,7 +298,10 @@ __global__ void __launch_bounds__(256)
       const float* sx = tiles->xyz[st];
       const float* sp = tiles->pn[st];
       const int tp = pipe.tile_points(t), t0 = t * kTilePoints;
-      for (int base = 0; base < tp; base += 32) {
+      bool done = false;
+      if (t == 0 && use_hist)
+        done = knn_first_tile_hist<CAP>(sx, sp, tp, cx, cy, cz, cn, k, lane, bkey, bidx, s_hist + warp * 256, count, thr);
+      for (int base = 0; base < tp && !done; base += 32) {
         const int p = base + lane;
         uint64_t key = kKeyMax;
         if (p < tp) {
@@ -317,7 +442,7 @@ template <int CAP, typename IdxT>
 int launch_knn(const float* xyz, const float* rgb, const float* centers, int B, int N, int G, int k, void* out_idx,
                float* out_neigh, float* out_feat, cudaStream_t st) {
   const int W = pick_warps(B, G);
-  const size_t smem = sizeof(TileSmem) + (size_t)W * CAP * 8;
+  const size_t smem = sizeof(TileSmem) + (size_t)W * CAP * 8 + (size_t)W * 256 * sizeof(int);
   const int use_bulk = (N % 4 == 0) && ((uintptr_t)xyz % 16 == 0);
   auto kern = knn_group_kernel<CAP, IdxT>;
   if (smem > 48 * 1024) {
@@ -328,7 +453,8 @@ int launch_knn(const float* xyz, const float* rgb, const float* centers, int B, 
     }
   }
   dim3 grid((G + W - 1) / W, B);
-  kern<<<grid, W * 32, smem, st>>>(xyz, rgb, centers, N, G, k, use_bulk, (IdxT*)out_idx, out_neigh, out_feat);
+  kern<<<grid, W * 32, smem, st>>>(xyz, rgb, centers, N, G, k, use_bulk, g_knn_hist >= 0 ? 1 : 0, (IdxT*)out_idx, out_neigh,
+                                   out_feat);
   return check_launch("ua_knn_group_f32");
 }
 

@@ -10,6 +10,7 @@
 // The M-step keeps the reference's operation order for the expanded-form variance (the part that cancels,
 // SURVEY H5); the two divisions by (c_new + 1e-10) become one correctly-rounded reciprocal per mode.
 #include "common.cuh"
+#include "modedota_params.cuh"
 
 namespace ua {
 
@@ -17,37 +18,9 @@ int g_modedota_threads = 0;  // tuning override
 int g_modedota_logprod = 1;  // tuning: 1 = product-form log-determinant in the single-sample path
 int g_modedota_groups = 0;   // tuning: warp groups per CTA of the single-sample path (0 = heuristic)
 int g_modedota_v = 0;        // tuning override: floats4 per lane of the single-sample path (-1 disables that path)
+int g_modedota_batch = 0;    // tuning: -1 disables the batched (cluster) path, N > 0 forces N D-splits
 
 namespace {
-
-constexpr int kMaxM = 16;
-constexpr int kMaxRows = 160;  // Bp + B rows of log-likelihoods kept in shared memory
-
-// Correctly-rounded reciprocal of a normal positive float whose reciprocal is normal: the fast path of
-// __frcp_rn (MUFU.RCP + one Newton step in FMA) without its range check and slow-path call, so that the
-// per-element chains of a thread stay branch-free and interleave.
-__device__ __forceinline__ float rcp_rn_normal(float v) {
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
-  const float e = -fmaf(v, r, -1.0f);
-  return fmaf(r, e, r);
-}
-
-struct StepParams {
-  const float* x_pred;  // [S,Bp,D] or null
-  const float* x_fit;   // [S,B,D] or null
-  const float* gamma;   // [S,B,ldg]
-  float* mu;
-  float* var;
-  float* pi;
-  float* c;
-  float* class_counts;
-  float* out_logits;  // [S,Bp,ldo]
-  int S, Bp, B, K, M, D;
-  int ldg, kg_off, ldo, ko_off;
-  float eps;
-  int use_bulk, stages, vec_ok;
-};
 
 template <int MM>
 __global__ void __launch_bounds__(MM > 8 ? 512 : 1024, 1) modedota_step_kernel(const StepParams p) {
@@ -694,6 +667,12 @@ extern "C" int ua_modedota_step_f32(const float* x_pred, int Bp, const float* x_
       }
       return check_launch("ua_modedota_step_f32(b1)");
     }
+  }
+
+  // ---- batched path: a cluster per class, feature axis split across its CTAs (modedota_batch.cu) ---------------
+  {
+    const int rc = modedota_batch_launch(p, st);
+    if (rc != 1) return rc;
   }
 
   int threads = g_modedota_threads > 0 ? g_modedota_threads : (D >= 1024 ? 1024 : 512);

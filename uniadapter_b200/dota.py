@@ -2,8 +2,9 @@
 same constructor, attributes (``mu, c, Sigma, overall_Sigma, Lambda, epsilon``) and methods (fit, update, predict).
 
 fit -> ua_dota_fit_f32 (one HBM pass over Sigma, class mean fused); predict -> ua_dota_predict_f16 (fp16 rounding
-points of the reference); update keeps a library inverse (cuSOLVER Cholesky + triangular solves: the matrix is SPD),
-fed by ua_dota_regularize_f32 (SURVEY §8f-3 lists a custom SPD inverse as a later row).
+points of the reference); update -> ua_dota_update_f32 (one cooperative launch, register-resident block
+Gauss-Jordan inverse of the SPD matrix, fp16 written directly). Feature widths the kernel does not take (D % 16 != 0
+or D > 1536) keep a library inverse (cuSOLVER Cholesky + triangular solves) fed by ua_dota_regularize_f32.
 """
 from __future__ import annotations
 
@@ -33,8 +34,10 @@ class DOTA(nn.Module):
         self.overall_Sigma = torch.mean(self.Sigma, dim=0).contiguous()
         # sigma*I is diagonal: its pseudo-inverse is the reciprocal diagonal (dota.py:31 uses pinverse in double)
         self.Lambda = torch.linalg.pinv(self.overall_Sigma.double()).half().contiguous()
-        self._reg = torch.empty_like(self.overall_Sigma)
-        self._eye = eye
+        ws = _lib.lib().ua_dota_update_workspace_bytes(input_shape) if input_shape % 16 == 0 and input_shape <= 1536 else -1
+        self._inv_ws = torch.empty(ws, dtype=torch.uint8, device=self.device) if ws > 0 else None
+        self._reg = torch.empty_like(self.overall_Sigma) if self._inv_ws is None else None
+        self._eye = eye if self._inv_ws is None else None
         if prior_pre_steps is not None:
             self.prior_pre_steps = prior_pre_steps
             self.update_prior = True
@@ -58,6 +61,13 @@ class DOTA(nn.Module):
 
     @torch.no_grad()
     def update(self):
+        if self._inv_ws is not None:
+            out = torch.empty((self.input_shape, self.input_shape), dtype=torch.float16, device=self.device)
+            rc = _lib.lib().ua_dota_update_f32(_lib.ptr(self.overall_Sigma), self.input_shape, float(self.epsilon),
+                                               _lib.ptr(self._inv_ws), _lib.ptr(out), None, _lib.stream_ptr())
+            _lib.check(rc, "ua_dota_update_f32")
+            self.Lambda = out
+            return
         rc = _lib.lib().ua_dota_regularize_f32(_lib.ptr(self.overall_Sigma), self.input_shape, float(self.epsilon),
                                                _lib.ptr(self._reg), _lib.stream_ptr())
         _lib.check(rc, "ua_dota_regularize_f32")
