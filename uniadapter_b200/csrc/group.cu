@@ -144,20 +144,74 @@ __device__ __forceinline__ void knn_compact(uint32_t* bkey, uint32_t* bidx, int&
 // ---- first tile by histogram selection -----------------------------------------------------------------------
 // The streaming filter starts blind: until the first compaction every point is a candidate, and each compaction is a
 // 32-step radix select over CAP register-held keys. For the first tile (<= 1024 points = 32 distances per lane, kept
-// in registers) the k-th smallest is found with one shared-memory histogram instead:
+// in registers) the k-th smallest is bracketed with one shared-memory histogram instead:
 //   bin(d) = min(255, (bits(max(d,0) + delta) - bits(delta)) >> 18),  delta = max_d / 64
 // is monotone in d (linear below delta, 32 bins per octave above: fine where the neighbours are, coarse in the far
-// tail); a warp scan over the 256 counters yields the bin b* that holds the k-th smallest, how many points lie in
-// lower bins, and how many share b* (a handful). Only those are radix-selected (usually one register per lane), and
-// one more pass over the registers emits the k survivors in ascending point-index order together with the exact
-// (key, index) threshold the streaming filter continues from. Exactness does not depend on the bin shape: bins only
-// pre-partition, the (distance bits, index) order decides. Returns false (nothing written) when b* holds more than
-// CAP points (e.g. all points identical): the caller then streams the tile as before.
-template <int CAP>
+// tail); a warp scan over the 256 counters yields the bin b* that holds the k-th smallest. Every point of a bin <= b*
+// is emitted to the candidate buffer in ascending index order (k + a handful), and the surplus -- the largest
+// (distance bits, index) pairs, all of them in bin b* -- is dropped by repeated warp-wide maxima (two REDUX each).
+// Exactness does not depend on the bin shape: bins only pre-partition, the (distance bits, index) order decides.
+// Returns false (nothing written) when the surplus is too large for that (e.g. many identical points): the caller then
+// streams the tile as before.
+constexpr int kMaxDrop = 12;
+
+// Removes the (count - k) largest (key, index) pairs from the buffer (stable), R registers per lane cover `count`.
+template <int R>
+__device__ __forceinline__ void knn_drop_largest(uint32_t* bkey, uint32_t* bidx, int& count, int k, int lane,
+                                                 bool want_thr, uint64_t& thr) {
+  __syncwarp();
+  uint32_t key[R], idx[R];
+  bool alive[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int e = r * 32 + lane;
+    alive[r] = e < count;
+    key[r] = alive[r] ? bkey[e] : 0u;
+    idx[r] = alive[r] ? bidx[e] : 0u;
+  }
+  const int ndrop = count - k;
+  for (int it = 0; it <= ndrop; ++it) {          // the last round only reads the k-th pair (the new threshold)
+    if (it == ndrop && !want_thr) break;
+    uint32_t bk = 0, bi = 0;
+    bool any = false;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const bool better = alive[r] && (!any || key[r] > bk || (key[r] == bk && idx[r] > bi));
+      if (better) bk = key[r], bi = idx[r], any = true;
+    }
+    const uint32_t mk = __reduce_max_sync(kFullMask, any ? bk : 0u);
+    const uint32_t mi = __reduce_max_sync(kFullMask, (any && bk == mk) ? bi : 0u);
+    if (it == ndrop) {
+      thr = ((uint64_t)mk << 32) | mi;
+    } else {
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (alive[r] && key[r] == mk && idx[r] == mi) alive[r] = false;
+    }
+  }
+  const unsigned lt_mask = (1u << lane) - 1u;
+  __syncwarp();
+  int out = 0;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const unsigned m = __ballot_sync(kFullMask, alive[r]);
+    if (alive[r]) {
+      const int pos = out + __popc(m & lt_mask);
+      bkey[pos] = key[r];
+      bidx[pos] = idx[r];
+    }
+    out += __popc(m);
+  }
+  __syncwarp();
+  count = out;  // == k
+}
+
+template <int CAP, bool FULL>
 __device__ __forceinline__ bool knn_first_tile_hist(const float* __restrict__ sx, const float* __restrict__ sp, int tp,
                                                     float cx, float cy, float cz, float cn, int k, int lane,
-                                                    uint32_t* bkey, uint32_t* bidx, int* hist, int& count,
-                                                    uint64_t& thr) {
+                                                    uint32_t* bkey, uint32_t* bidx, int* hist, bool more_tiles,
+                                                    int& count, uint64_t& thr) {
+  constexpr int RD = CAP == 128 ? 2 : (CAP == 256 ? 4 : 5);   // registers per lane that cover k + kMaxDrop candidates
   const unsigned lt_mask = (1u << lane) - 1u;
   float d[32];
   float dm = 0.f;
@@ -165,7 +219,7 @@ __device__ __forceinline__ bool knn_first_tile_hist(const float* __restrict__ sx
   for (int r = 0; r < 32; ++r) {
     const int p = r * 32 + lane;
     d[r] = INFINITY;
-    if (p < tp) {
+    if (FULL || p < tp) {
       d[r] = expanded_sqdist(cx, cy, cz, cn, sx[3 * p], sx[3 * p + 1], sx[3 * p + 2], sp[p]);
       dm = fmaxf(dm, d[r]);
     }
@@ -173,16 +227,18 @@ __device__ __forceinline__ bool knn_first_tile_hist(const float* __restrict__ sx
   const float dmax = __uint_as_float(__reduce_max_sync(kFullMask, __float_as_uint(dm)));   // dm >= 0: bits are ordered
   const float delta = dmax * 0.015625f;
   const uint32_t dbits = __float_as_uint(delta);
-  auto bin_of = [&](float v) -> uint32_t {
-    const uint32_t e = __float_as_uint(__fadd_rn(fmaxf(v, 0.f), delta)) - dbits;
-    return min(e >> 18, 255u);
-  };
 #pragma unroll
   for (int j = 0; j < 8; ++j) hist[lane + 32 * j] = 0;
   __syncwarp();
+  const uint32_t hist_s = smem_u32(hist);
 #pragma unroll
   for (int r = 0; r < 32; ++r)
-    if (r * 32 + lane < tp) atomicAdd(&hist[bin_of(d[r])], 1);
+    if (FULL || r * 32 + lane < tp) {
+      const uint32_t e = __float_as_uint(__fadd_rn(fmaxf(d[r], 0.f), delta)) - dbits;
+      const uint32_t bin = min(e >> 18, 255u);
+      // plain shared-memory reduction (the compiler would turn atomicAdd into a 30-instruction match-and-aggregate loop)
+      asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist_s + 4u * bin) : "memory");
+    }
   __syncwarp();
   // warp scan over the 256 counters (8 per lane)
   int h[8];
@@ -201,62 +257,37 @@ __device__ __forceinline__ bool knn_first_tile_hist(const float* __restrict__ sx
   }
   const unsigned mb = __ballot_sync(kFullMask, incl >= k);      // tp >= k, so some lane crosses
   const int L = __ffs(mb) - 1;
-  int bstar = 0, nless = 0, neq = 0;
+  int bstar = 0, upto = 0;                                      // upto = points in bins <= b*
   if (lane == L) {
     int c = incl - ssum;
     bool found = false;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      if (!found && c + h[j] >= k) bstar = 8 * lane + j, nless = c, neq = h[j], found = true;
       c += h[j];
+      if (!found && c >= k) bstar = 8 * lane + j, upto = c, found = true;
     }
   }
   bstar = __shfl_sync(kFullMask, bstar, L);
-  nless = __shfl_sync(kFullMask, nless, L);
-  neq = __shfl_sync(kFullMask, neq, L);
-  if (neq > CAP) return false;
-  // the points of bin b*, in index order, into the candidate buffer
-  int cnt = 0;
-#pragma unroll
-  for (int r = 0; r < 32; ++r) {
-    const int p = r * 32 + lane;
-    const bool eq = p < tp && bin_of(d[r]) == (uint32_t)bstar;
-    const unsigned m = __ballot_sync(kFullMask, eq);
-    if (m) {
-      if (eq) {
-        const int pos = cnt + __popc(m & lt_mask);
-        bkey[pos] = float_to_ordered(d[r]);
-        bidx[pos] = (uint32_t)p;
-      }
-      cnt += __popc(m);
-    }
-  }
-  // the (k - nless)-th smallest (key, index) among them is the k-th smallest of the tile
-  uint64_t t2;
-  const int need = k - nless;
-  if (neq <= 32) knn_compact<32>(bkey, bidx, cnt, need, lane, t2);
-  else if (neq <= 64) knn_compact<64>(bkey, bidx, cnt, need, lane, t2);
-  else knn_compact<CAP>(bkey, bidx, cnt, need, lane, t2);
-  const uint32_t T = (uint32_t)(t2 >> 32), ti = (uint32_t)t2;
+  upto = __shfl_sync(kFullMask, upto, L);
+  if (upto - k > kMaxDrop) return false;
+  // every point of a bin <= b*, in index order, into the candidate buffer: bits(max(d,0) + delta) < ub
+  const uint32_t ub = bstar >= 255 ? 0xffffffffu : dbits + ((uint32_t)(bstar + 1) << 18);
   int out = 0;
 #pragma unroll
   for (int r = 0; r < 32; ++r) {
     const int p = r * 32 + lane;
-    const uint32_t key = float_to_ordered(d[r]);
-    const bool take = p < tp && (key < T || (key == T && (uint32_t)p <= ti));
+    const bool take = (FULL || p < tp) && __float_as_uint(__fadd_rn(fmaxf(d[r], 0.f), delta)) < ub;
     const unsigned m = __ballot_sync(kFullMask, take);
-    if (m) {
-      if (take) {
-        const int pos = out + __popc(m & lt_mask);
-        bkey[pos] = key;
-        bidx[pos] = (uint32_t)p;
-      }
-      out += __popc(m);
+    if (take) {
+      const int pos = out + __popc(m & lt_mask);
+      bkey[pos] = float_to_ordered(d[r]);
+      bidx[pos] = (uint32_t)p;
     }
+    out += __popc(m);
   }
+  count = out;  // == upto
+  if (count > k || more_tiles) knn_drop_largest<RD>(bkey, bidx, count, k, lane, more_tiles, thr);
   __syncwarp();
-  count = out;  // == k
-  thr = t2;
   return true;
 }
 
@@ -299,8 +330,13 @@ __global__ void __launch_bounds__(256)
       const float* sp = tiles->pn[st];
       const int tp = pipe.tile_points(t), t0 = t * kTilePoints;
       bool done = false;
-      if (t == 0 && use_hist)
-        done = knn_first_tile_hist<CAP>(sx, sp, tp, cx, cy, cz, cn, k, lane, bkey, bidx, s_hist + warp * 256, count, thr);
+      if (t == 0 && use_hist) {
+        int* hist = s_hist + warp * 256;
+        const bool more = pipe.ntiles > 1;
+        done = tp == kTilePoints
+                   ? knn_first_tile_hist<CAP, true>(sx, sp, tp, cx, cy, cz, cn, k, lane, bkey, bidx, hist, more, count, thr)
+                   : knn_first_tile_hist<CAP, false>(sx, sp, tp, cx, cy, cz, cn, k, lane, bkey, bidx, hist, more, count, thr);
+      }
       for (int base = 0; base < tp && !done; base += 32) {
         const int p = base + lane;
         uint64_t key = kKeyMax;
