@@ -227,9 +227,10 @@ def run_ours(args):
     summ = tl.summary()
     _lib.enable_kernel_timing(False)
     G, kk = 512, 32
+    V = 2 if engine.batch_views else 1      # clouds per stream in one tokenizer / encoder launch (sample + jittered view)
     alg_bytes = {   # algorithmic bytes per launch
-        "ua_fps_f32": S * (N_POINTS * 12 + G * 12),
-        "ua_knn_group_f32": S * (N_POINTS * 12 + G * 12 + G * kk * 12),
+        "ua_fps_f32": V * S * (N_POINTS * 12 + G * 12),
+        "ua_knn_group_f32": V * S * (N_POINTS * 12 + G * 12 + G * kk * 12),
         "ua_head_f32": 4 * S * (FEAT_DIM + FEAT_DIM * N_CLASSES + N_CLASSES),
         "ua_modedota_step_f32": 16 * S * N_CLASSES * MODES * FEAT_DIM,
         "ua_fuse_logits_f32": 4 * S * 3 * N_CLASSES,

@@ -65,17 +65,20 @@ def replay_rng(T, N):
     return seq
 
 
+@pytest.mark.parametrize("batch_views", [True, False])
 @pytest.mark.parametrize("name", ["e2e_ulip_d2_modedota_res", "e2e_ulip_d2_modedota"])
-def test_stream_engine_vs_reference_loop(name, cuda_device):
+def test_stream_engine_vs_reference_loop(name, batch_views, cuda_device):
     """The lock-step engine (stacked state, multi-text head, two-GEMM residual learning) on 3 streams fed the same
-    stream: every stream must reproduce the reference loop."""
+    stream: every stream must reproduce the reference loop, whether the sample and its jittered view go through the
+    encoder as one batch of 2S clouds (default) or one after the other (the reference's order)."""
     from uniadapter_b200.engine import StreamEngine
     inp = cases.e2e_inputs(name)
     gold = load_golden(name, inp)
     dev = cuda_device
     S = 3
     eng = StreamEngine(build(inp, dev, tensor_cores=True), 'ulip', torch.from_numpy(inp["text"]), S, inp["N"], cases.CFG,
-                       mode_M=inp["M"], res_learning=inp["res_learning"], device=dev, use_graph=False)
+                       mode_M=inp["M"], res_learning=inp["res_learning"], device=dev, use_graph=False,
+                       batch_views=batch_views)
     pcs = torch.from_numpy(inp["pc"])
     for i, (s0, noise, s1) in enumerate(replay_rng(inp["T"], inp["N"])):
         eng.inject = dict(start=s0.expand(S).contiguous().to(dev), noise=noise.expand(S, -1, -1).contiguous().to(dev),

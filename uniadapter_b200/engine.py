@@ -61,7 +61,7 @@ class StreamEngine:
     """
 
     def __init__(self, encoder, vlm3d, text, num_streams, npoints, cfg, mode_M=8, res_learning=True, device='cuda',
-                 use_graph=True, colored=False, seed=42):
+                 use_graph=True, colored=False, seed=42, batch_views=True):
         self.dev = torch.device(device)
         self.encoder, self.vlm3d = encoder, vlm3d
         self.S, self.N = num_streams, npoints
@@ -71,6 +71,7 @@ class StreamEngine:
         self.res_learning = res_learning
         self.use_graph = use_graph
         self.colored = colored
+        self.batch_views = batch_views      # both views of a step through the encoder as one batch of 2S clouds
         S, N, K, D = self.S, self.N, self.K, self.D
         self.adapter = MultiStreamModeDota(cfg, D, K, self.text0, mode_M, S, self.dev)
         # static buffers
@@ -94,12 +95,13 @@ class StreamEngine:
         self._host_out = torch.empty(S, K, dtype=torch.float32).pin_memory() if self.dev.type == 'cuda' else None
 
     # ---- pieces of the step ------------------------------------------------------------------------------------
-    def _encode(self, pc):
+    def _encode(self, pc, rgb=None):
+        rgb = self.rgb if rgb is None else rgb
         if self.vlm3d == 'uni3d':
-            return self.encoder.encode_pc(torch.cat((pc, self.rgb), dim=-1))
+            return self.encoder.encode_pc(torch.cat((pc, rgb), dim=-1))
         if self.vlm3d == 'ulip':
             return self.encoder(pc)
-        return self.encoder(pc, torch.cat((pc, self.rgb), dim=-1))
+        return self.encoder(pc, torch.cat((pc, rgb), dim=-1))
 
     def _set_start(self, start):
         if start is not None:
@@ -109,18 +111,31 @@ class StreamEngine:
 
     @torch.no_grad()
     def _adapt(self):
-        """Tokenizer + encoder (x2), head, cache predict+fit, fit on the augmented view, fusion."""
+        """Tokenizer + encoder, head, cache predict+fit, fit on the augmented view, fusion.
+
+        The reference encodes the sample, adapts, then encodes the jittered copy (Uni_Adapter.py:401-431). The jittered
+        cloud depends only on the input, so both views go through the tokenizer and the encoder as ONE batch of 2S
+        clouds (per-cloud results are unchanged: every kernel of the pass is independent across clouds); the two cache
+        steps keep the reference's order."""
         S, K = self.S, self.K
         inj = self.inject or {}
-        self._set_start(inj.get('start'))
-        feats, clip_logits, _, prob, _ = zero_shot_head(self._encode(self.pc), self.text)
+        noise = inj['noise'] if 'noise' in inj else torch.randn_like(self.pc)
+        pc2 = torch.cat((self.pc, self.pc + 0.05 * noise), dim=0)          # Uni_Adapter.py:420-421
+        if self.batch_views:
+            if inj.get('start') is not None and inj.get('start_aug') is not None:
+                self._set_start(torch.cat((inj['start'], inj['start_aug'])))
+            emb = self._encode(pc2, torch.cat((self.rgb, self.rgb), dim=0))
+            emb, emb_aug = emb[:S], emb[S:]
+        else:
+            self._set_start(inj.get('start'))
+            emb = self._encode(pc2[:S])
+            self._set_start(inj.get('start_aug'))
+            emb_aug = self._encode(pc2[S:])
+        feats, clip_logits, _, prob, _ = zero_shot_head(emb, self.text)
         x_fit = feats.unsqueeze(1)                                     # (S,1,D): batch 1 per stream
         x_pred = x_fit.half().float()                                  # Uni_Adapter.py:416 rounds through fp16
         self.adapter.step(x_pred, x_fit, prob.unsqueeze(1), self.dota_logits)
-        noise = inj['noise'] if 'noise' in inj else torch.randn_like(self.pc)
-        pc_aug = self.pc + 0.05 * noise                                 # Uni_Adapter.py:420-421
-        self._set_start(inj.get('start_aug'))
-        feats_aug, _, _, _, _ = zero_shot_head(self._encode(pc_aug), self.text)
+        feats_aug, _, _, _, _ = zero_shot_head(emb_aug, self.text)
         self.adapter.step(None, feats_aug.unsqueeze(1), prob.unsqueeze(1))
         self._clip_logits = clip_logits
 
