@@ -102,6 +102,13 @@ def test_full_size_tokenizer_vs_oracle(B, N, G, k, start, cuda_device):
     assert idx.dtype == torch.int32
     o_fps = T.fps(xyz_np, G, st, threads=8)
     np.testing.assert_array_equal(idx.cpu().numpy().astype(np.int64), o_fps)
+    from uniadapter_b200 import _lib
+    _lib.set_tuning("fps_cluster", -1)          # one CTA per cloud (the cluster path serves few clouds of > 2048 points)
+    try:
+        idx1, centers1 = ua.fps_sample(xyz, G, None if st is None else cu(st, cuda_device), idx_dtype=torch.int32)
+    finally:
+        _lib.set_tuning("fps_cluster", 0)
+    assert torch.equal(idx, idx1) and torch.equal(centers, centers1)
     kidx, neigh, _ = knn_both_paths(xyz, centers, k)
     o_idx = np.sort(T.knn(xyz_np, centers.cpu().numpy(), k, threads=8), axis=-1)
     np.testing.assert_array_equal(kidx.cpu().numpy(), o_idx)
@@ -121,6 +128,35 @@ def test_knn_with_many_identical_points(N, k, ndup, cuda_device):
     o_idx = np.sort(T.knn(xyz_np, centers_np, k, threads=2), axis=-1)
     np.testing.assert_array_equal(kidx.cpu().numpy(), o_idx)
     np.testing.assert_array_equal(kidx.cpu().numpy()[0, 0], np.arange(k) if k <= ndup else kidx.cpu().numpy()[0, 0])
+
+
+@pytest.mark.parametrize("B,N,G,skip", [(3, 257, 40, False), (2, 5, 5, False), (1, 3000, 700, True), (5, 2049, 64, False),
+                                         (2, 300, 64, False)])
+def test_fps_cluster_path_small_and_ragged(B, N, G, skip, cuda_device):
+    """The cluster FPS (one 8-CTA cluster per cloud, candidates exchanged through distributed shared memory) forced
+    onto small, ragged and duplicated clouds: empty slices, ties across slices, the near-origin skip."""
+    import uniadapter_b200 as ua
+    from uniadapter_b200 import _lib
+    from oracle import synth
+    xyz_np = synth.cloud(B, N, 77 + N)
+    if N == 300:
+        xyz_np[:, 100:200] = xyz_np[:, 0:100]        # every point three times: ties across slices
+        xyz_np[:, 200:300] = xyz_np[:, 0:100]
+    if skip:
+        xyz_np[:, ::7] *= 0.01                        # points inside the 1e-3 ball are never selected
+    st = synth.integers(0, N, (B,), 9)
+    xyz = cu(xyz_np, cuda_device)
+    outs = []
+    for mode in (1, -1):
+        _lib.set_tuning("fps_cluster", mode)
+        try:
+            outs.append(ua.fps_sample(xyz, G, None if skip else cu(st, cuda_device), skip_small_norm=skip))
+        finally:
+            _lib.set_tuning("fps_cluster", 0)
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    if not skip:
+        np.testing.assert_array_equal(outs[0][0].cpu().numpy().astype(np.int64), T.fps(xyz_np, G, st, threads=2))
+    np.testing.assert_array_equal(outs[0][1].cpu().numpy(), T.gather(xyz_np, outs[0][0].cpu().numpy().astype(np.int64)))
 
 
 def test_uni3d_entry_points_and_skip_small_norm(cuda_device):

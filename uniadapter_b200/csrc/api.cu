@@ -10,6 +10,8 @@ static thread_local char g_err[512] = "";
 static std::atomic<int64_t> g_launches{0};
 
 extern int g_fps_threads;
+extern int g_dota_ksplit;
+extern int g_fps_cluster;
 extern int g_knn_warps;
 extern int g_knn_hist;
 extern int g_modedota_threads;
@@ -50,6 +52,8 @@ extern "C" void ua_reset_launch_count(void) { ua::g_launches.store(0); }
 extern "C" int ua_set_tuning(const char* key, int value) {
   if (!key) return UA_ERR_INVALID_ARG;
   if (!strcmp(key, "fps_threads")) { ua::g_fps_threads = value; return UA_OK; }
+  if (!strcmp(key, "dota_ksplit")) { ua::g_dota_ksplit = value; return UA_OK; }
+  if (!strcmp(key, "fps_cluster")) { ua::g_fps_cluster = value; return UA_OK; }
   if (!strcmp(key, "knn_warps")) { ua::g_knn_warps = value; return UA_OK; }
   if (!strcmp(key, "knn_hist")) { ua::g_knn_hist = value; return UA_OK; }
   if (!strcmp(key, "modedota_threads")) { ua::g_modedota_threads = value; return UA_OK; }

@@ -4,27 +4,40 @@
 // fit is a pure HBM stream over Sigma [K,D,D] (read + write once, 8*K*D^2 bytes): each thread owns one float4 of a
 // (row, 4 columns) position and walks the K classes, applying the rank-B update and accumulating the class mean
 // (overall_Sigma) on the fly, so neither delta (K,D,D) nor a second pass for the mean ever touch memory.
+#include <cooperative_groups.h>
 #include "common.cuh"
 
+namespace cg = cooperative_groups;
+
 namespace ua {
+
+int g_dota_ksplit = 0;   // tuning: class splits (cluster size) of the fit kernel, 0 = heuristic
+
 namespace {
 
 constexpr int kTileRows = 8;     // rows of Sigma per CTA
 constexpr int kTileCols = 128;   // columns per CTA (32 threads x float4)
 
-// grid: (ceil(D/128), ceil(D/8)); block: (32, 8)
+// grid: (ceil(D/128), ceil(D/8), KS); block: (32, 8); cluster (1, 1, KS).
+// The K classes are split over the KS CTAs of a thread-block cluster (at D = 512 a grid of tiles alone is 256 CTAs:
+// a fifth of the machine's thread slots, too few loads in flight for HBM); each CTA streams its classes and keeps the
+// partial class sum of its tile in registers, the partials meet in rank 0 through distributed shared memory in rank
+// order (deterministic), which writes overall_Sigma. KS = 1 runs without a cluster.
 __global__ void __launch_bounds__(256)
     dota_sigma_kernel(const float* __restrict__ x, const float* __restrict__ y, int B, const float* __restrict__ mu,
                       const float* __restrict__ c, float* __restrict__ Sigma, float* __restrict__ overall, int K,
                       int D) {
+  __shared__ __align__(16) float4 s_partial[256];
+  const int KS = (int)gridDim.z, ks = (int)blockIdx.z;
   const int j = blockIdx.x * kTileCols + threadIdx.x * 4;
   const int i = blockIdx.y * kTileRows + threadIdx.y;
-  if (i >= D || j >= D) return;
+  const bool inside = i < D && j < D;
   float4 mean = make_float4(0.f, 0.f, 0.f, 0.f);
   const size_t DD = (size_t)D * D;
-  float* sp = Sigma + (size_t)i * D + j;
+  float* sp = Sigma + (size_t)(inside ? i : 0) * D + (inside ? j : 0);
+  const int kper = (K + KS - 1) / KS, k_begin = ks * kper, k_end = min(K, k_begin + kper);
 #pragma unroll 4
-  for (int k = 0; k < K; ++k) {
+  for (int k = k_begin; k < k_end && inside; ++k) {
     const float4 sg = *reinterpret_cast<const float4*>(sp + (size_t)k * DD);
     const float mi = __ldg(mu + (size_t)k * D + i);
     const float4 mj = __ldg(reinterpret_cast<const float4*>(mu + (size_t)k * D + j));
@@ -62,6 +75,21 @@ __global__ void __launch_bounds__(256)
     *reinterpret_cast<float4*>(sp + (size_t)k * DD) = out;
     mean.x += out.x, mean.y += out.y, mean.z += out.z, mean.w += out.w;
   }
+  if (KS > 1) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int t = threadIdx.y * 32 + threadIdx.x;
+    s_partial[t] = mean;
+    cluster.sync();
+    if (ks == 0) {
+      for (int r = 1; r < KS; ++r) {
+        const float4 p = cluster.map_shared_rank(s_partial, r)[t];
+        mean.x += p.x, mean.y += p.y, mean.z += p.z, mean.w += p.w;
+      }
+    }
+    cluster.sync();      // peers keep their partials alive until rank 0 has read them
+    if (ks != 0) return;
+  }
+  if (!inside) return;
   const float kf = (float)K;
   float4 m4 = make_float4(__fdiv_rn(mean.x, kf), __fdiv_rn(mean.y, kf), __fdiv_rn(mean.z, kf), __fdiv_rn(mean.w, kf));
   *reinterpret_cast<float4*>(overall + (size_t)i * D + j) = m4;
@@ -168,8 +196,27 @@ extern "C" int ua_dota_fit_f32(const float* x, const float* y, int B, float* mu,
   UA_REQUIRE(B >= 1 && K >= 1 && D >= 1, "ua_dota_fit_f32: bad sizes B=%d K=%d D=%d", B, K, D);
   UA_UNSUPPORTED((D & 3) != 0, "ua_dota_fit_f32: D=%d must be a multiple of 4", D);
   cudaStream_t st = (cudaStream_t)stream;
-  dim3 grid((D + kTileCols - 1) / kTileCols, (D + kTileRows - 1) / kTileRows), block(32, kTileRows);
-  dota_sigma_kernel<<<grid, block, 0, st>>>(x, y, B, mu, c, Sigma, overall, K, D);
+  const int tiles = ((D + kTileCols - 1) / kTileCols) * ((D + kTileRows - 1) / kTileRows);
+  // class splits: two when the tile grid alone is under two CTAs per SM (D = 512: 40 -> 30 us; measured sweep in
+  // tools/probe_dota_fit.py: more splits, or any split at D >= 1024, lose to the extra cluster barrier)
+  int KS = g_dota_ksplit > 0 ? g_dota_ksplit : ((tiles < 2 * kNumSMs && K >= 8) ? 2 : 1);
+  if (KS > K) KS = 1;
+  dim3 grid((D + kTileCols - 1) / kTileCols, (D + kTileRows - 1) / kTileRows, KS), block(32, kTileRows);
+  if (KS == 1) {
+    dota_sigma_kernel<<<grid, block, 0, st>>>(x, y, B, mu, c, Sigma, overall, K, D);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = 0, cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = (unsigned)KS;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, dota_sigma_kernel, x, y, B, (const float*)mu, (const float*)c, Sigma, overall, K, D);
+    if (e != cudaSuccess) {
+      set_error("ua_dota_fit_f32: cluster launch failed: %s", cudaGetErrorString(e));
+      return UA_ERR_CUDA;
+    }
+  }
   int rc = check_launch("ua_dota_fit_f32(sigma)");
   if (rc != UA_OK) return rc;
   dota_mean_kernel<<<K, 256, 0, st>>>(x, y, B, mu, c, K, D);
