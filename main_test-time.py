@@ -60,11 +60,17 @@ def parse_args(argv=None):
     p.add_argument('--num-classes', type=int, default=40, help='classes of the synthetic stream / text features')
     p.add_argument('--stream-length', type=int, default=64, help='samples per synthetic corruption stream')
     p.add_argument('--small-encoder', action='store_true', help='2 transformer blocks (smoke runs)')
+    p.add_argument('--lockstep', action=argparse.BooleanOptionalAction, default=None,
+                   help='advance the corruption streams of this rank together, one CUDA-graph step per sample index '
+                        '(default: on for --use-mode-dota at batch size 1); --no-lockstep walks them one after the '
+                        'other like the reference')
     args = p.parse_args(argv)
     if args.use_dota and args.use_mode_dota and '--use-mode-dota' not in (argv or sys.argv):
         args.use_mode_dota = False          # --use-dota alone selects the DOTA branch (reachable here, unlike upstream)
     if not args.use_mode_dota:
         args.res_learning = False
+    if args.lockstep is None:
+        args.lockstep = bool(args.use_mode_dota) and args.batch_size == 1 and args.vlm3d != 'openshape'
     return args
 
 
@@ -106,6 +112,20 @@ def main(argv=None):
     corruptions = CORRUPTIONS if args.corruption == 'all' else [args.corruption]
     mine = parallel.assign_streams(len(corruptions), world, rank)
     local_results = {}
+    if args.lockstep and mine:
+        from uniadapter_b200.adapter import test_zeroshot_3d_lockstep
+        datasets = [NpyCorruptionStream(args.myroot, corruptions[s], args.severity, npoints=args.npoints) if args.myroot else
+                    SyntheticStream(args.stream_length, args.npoints, args.num_classes, seed=args.seed, stream=s)
+                    for s in mine]
+        results = test_zeroshot_3d_lockstep(datasets, model, args, names=[corruptions[s] for s in mine])
+        for s, result in zip(mine, results):
+            local_results[s] = result
+            if world > 1 or rank == 0:
+                print(f"[rank {rank}] {corruptions[s]}: acc1 {result['acc1']:.2f} acc3 {result['acc3']:.2f} acc5 "
+                      f"{result['acc5']:.2f} ({result['ms_per_sample']:.3f} ms/sample incl. warm-up and graph capture, median "
+                      f"{result['median_ms_per_sample']:.3f}; {len(mine)} streams in lock-step)",
+                      flush=True)
+        mine = []
     for s in mine:
         corr = corruptions[s]
         args.corruption = corr

@@ -27,7 +27,8 @@ def test_flags_follow_the_reference_and_fix_d1():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("flags", [['--mode-M', '8'], ['--use-dota'], ['--mode-M', '4', '--no-res-learning']])
+@pytest.mark.parametrize("flags", [['--mode-M', '8'], ['--use-dota'], ['--mode-M', '4', '--no-res-learning'],
+                                   ['--mode-M', '8', '--no-lockstep']])
 def test_cli_runs_a_stream_on_the_gpu(flags, cuda_device, tmp_path):
     m = load_main()
     out = m.main(['--vlm3d', 'ulip', '--small-encoder', '--corruption', 'gaussian', '--stream-length', '5',
@@ -49,3 +50,22 @@ def test_cli_other_encoder_families(family, cuda_device, tmp_path):
                   str(tmp_path)])
     (res,) = out.values()
     assert len(res['times_ms']) == 3 and int(res['preds'].max()) < classes
+
+
+@pytest.mark.gpu
+def test_cli_all_corruptions_in_lockstep(cuda_device, tmp_path):
+    """--corruption all: the 15 independent corruption streams advance together (one CUDA-graph step per sample index,
+    uniadapter_b200.adapter.test_zeroshot_3d_lockstep); every stream reports its own accuracies and predictions."""
+    m = load_main()
+    a = m.parse_args(['--vlm3d', 'ulip'])
+    assert a.lockstep and not m.parse_args(['--use-dota']).lockstep and not m.parse_args(['--batch-size', '4']).lockstep
+    out = m.main(['--vlm3d', 'ulip', '--small-encoder', '--corruption', 'all', '--stream-length', '6', '--num-classes',
+                  '12', '--mode-M', '8', '--output-dir', str(tmp_path)])
+    assert len(out) == 15
+    for res in out.values():
+        assert 0.0 <= res['acc1'] <= res['acc3'] <= res['acc5'] <= 100.0
+        assert res['preds'].shape == (6,) and len(res['times_ms']) == 6
+    # streams differ (own data, own adapter state): not all prediction rows are equal
+    import torch
+    rows = torch.stack([r['preds'] for r in out.values()])
+    assert (rows != rows[0]).any()

@@ -140,3 +140,59 @@ def test_zeroshot_3d_core(test_loader, validate_dataset_name, model, clip_model,
     return {'acc1': top1.avg, 'acc3': top3.avg, 'acc5': top5.avg, 'times_ms': stored_times,
             'preds': torch.cat(preds) if preds else torch.empty(0, dtype=torch.long), 'adapter': adapter,
             'logits': torch.cat(all_logits) if all_logits else None}
+
+
+def test_zeroshot_3d_lockstep(datasets, model, args, names=None):
+    """The same per-sample adaptation loop for S independent corruption streams, advanced in lock-step on one GPU.
+
+    The reference builds a fresh adapter per corruption and walks the corruptions one after the other
+    (main_test-time.py:68-98, Uni_Adapter.py:328-339), one sample per step: ~300 tiny launches per sample, the GPU idle
+    between them. The streams do not interact, so here sample i of every stream forms one step of
+    ``engine.StreamEngine``: one tokenizer / encoder pass over 2S clouds (sample + jittered view), one cache launch over
+    the stacked state [S,K,M,D], one residual-learning call for S streams, the whole step replayed as a CUDA graph.
+    With one dataset this is the per-sample loop of ``test_zeroshot_3d_core`` as a captured graph.
+
+    MODE-DOTA only (``--use-mode-dota``, with or without ``--res-learning``), batch size 1, rgb = ones (what every
+    dataset class of the reference returns). Returns one result dict per stream (acc1/acc3/acc5 in percent, preds) plus
+    the per-step device times (reference event placement: host->device copy to fused logits)."""
+    from .engine import StreamEngine
+    from .streams import PinnedPrefetcher
+    device = torch.device(args.device)
+    if not args.use_mode_dota:
+        raise NotImplementedError("lock-step streams run the MODE-DOTA path; use test_zeroshot_3d_core for --use-dota")
+    cfg = {'epsilon': args.dota_epsilon, 'sigma': args.dota_sigma, 'eta': args.dota_eta, 'rho': args.dota_rho}
+    text = load_text_features(args, device)
+    S = len(datasets)
+    engine = StreamEngine(model, args.vlm3d, text, S, args.npoints, cfg, mode_M=args.mode_M,
+                          res_learning=bool(args.res_learning), device=device, use_graph=True, seed=args.seed)
+    feed = PinnedPrefetcher(datasets, args.npoints)
+    hits = torch.zeros(S, 3)
+    preds, times = [], []
+    start_event, end_event = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 0
+    for pc_host, labels in feed:
+        torch.cuda.synchronize()
+        start_event.record()
+        final, _ = engine.step(pc_host)                      # (S,K) pinned host logits; synchronised on return
+        end_event.record()
+        torch.cuda.synchronize()
+        times.append(start_event.elapsed_time(end_event))
+        top = final.topk(min(5, final.shape[1]), dim=1).indices          # (S,5)
+        match = top.eq(labels.view(-1, 1))
+        hits[:, 0] += match[:, :1].any(1).float()
+        hits[:, 1] += match[:, :3].any(1).float()
+        hits[:, 2] += match[:, :5].any(1).float()
+        preds.append(top[:, 0].clone())
+        n += 1
+        if n % max(1, args.print_freq) == 0:
+            logging.info(f"Test: [{n}/{feed.length}] Acc@1 {100 * float(hits[:, 0].mean()) / n:.2f} "
+                         f"({times[-1] / S:.3f} ms/sample)")
+    preds = torch.stack(preds, 1) if preds else torch.empty(S, 0, dtype=torch.long)
+    out = []
+    for s in range(S):
+        acc = (100.0 * hits[s] / max(n, 1)).tolist()
+        out.append({'acc1': acc[0], 'acc3': acc[1], 'acc5': acc[2], 'preds': preds[s], 'times_ms': times,
+                    'ms_per_sample': (sum(times) / max(n, 1)) / S,
+                    'median_ms_per_sample': (sorted(times)[len(times) // 2] / S) if times else float('nan'),
+                    'name': names[s] if names else str(s)})
+    return out

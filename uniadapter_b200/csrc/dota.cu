@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(256)
   float* sp = Sigma + (size_t)(inside ? i : 0) * D + (inside ? j : 0);
   const int kper = (K + KS - 1) / KS, k_begin = ks * kper, k_end = min(K, k_begin + kper);
 #pragma unroll 4
-  for (int k = k_begin; k < k_end && inside; ++k) {
+  for (int k = inside ? k_begin : k_end; k < k_end; ++k) {
     const float4 sg = *reinterpret_cast<const float4*>(sp + (size_t)k * DD);
     const float mi = __ldg(mu + (size_t)k * D + i);
     const float4 mj = __ldg(reinterpret_cast<const float4*>(mu + (size_t)k * D + j));
@@ -197,9 +197,11 @@ extern "C" int ua_dota_fit_f32(const float* x, const float* y, int B, float* mu,
   UA_UNSUPPORTED((D & 3) != 0, "ua_dota_fit_f32: D=%d must be a multiple of 4", D);
   cudaStream_t st = (cudaStream_t)stream;
   const int tiles = ((D + kTileCols - 1) / kTileCols) * ((D + kTileRows - 1) / kTileRows);
-  // class splits: two when the tile grid alone is under two CTAs per SM (D = 512: 40 -> 30 us; measured sweep in
-  // tools/probe_dota_fit.py: more splits, or any split at D >= 1024, lose to the extra cluster barrier)
-  int KS = g_dota_ksplit > 0 ? g_dota_ksplit : ((tiles < 2 * kNumSMs && K >= 8) ? 2 : 1);
+  // class splits (cluster size): off by default. The sweep in tools/probe_dota_fit.py shows no reliable gain on B200
+  // (D = 512: 38-40 us unsplit, 30-42 us with two splits depending on the box; D >= 1024: always slower): the
+  // kernel is limited by its per-thread chain of dependent 16-byte loads, not by the number of CTAs.
+  (void)tiles;
+  int KS = g_dota_ksplit > 0 ? g_dota_ksplit : 1;
   if (KS > K) KS = 1;
   dim3 grid((D + kTileCols - 1) / kTileCols, (D + kTileRows - 1) / kTileRows, KS), block(32, kTileRows);
   if (KS == 1) {
