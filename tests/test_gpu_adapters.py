@@ -420,3 +420,26 @@ def test_class_sharded_cache_emulated_ranks(P_, cuda_device):
         assert torch.equal(sh.ops.cache.mu[0], full.mu[sh.k_lo:sh.k_hi])
         assert torch.equal(sh.ops.cache.var[0], full.var[sh.k_lo:sh.k_hi])
         assert torch.equal(sh.ops.cache.c[0], full.c[sh.k_lo:sh.k_hi])
+
+
+def test_class_sharded_step_as_cuda_graph(cuda_device):
+    """ShardedModeDota.step_graphed (world 1: the gather is a device copy) replays the eager step exactly: same logits,
+    same prediction, same cache state as a second object stepped eagerly; the soft-count sum lives on the device."""
+    import uniadapter_b200 as ua
+    from uniadapter_b200 import parallel as PP
+    from oracle import synth
+    K, M, D, T = 77, 8, 256, 7
+    cfg = cases.CFG
+    dev = cuda_device
+    text = torch.from_numpy(synth.unit_rows(K, D, 17)).to(dev)
+    x, xa, _ = synth.features(T, 1, D, text.cpu().numpy(), 18)
+    x, xa = cu(x * np.float32(2.5), dev), cu(xa * np.float32(1.5), dev)
+    mk = lambda: PP.ShardedModeDota(cfg, text, M, lambda ts: PP.CudaShardOps(cfg, D, ts, M, dev), rank=0, world=1)
+    eager, graphed = mk(), mk()
+    for t in range(T):
+        a = eager.step(x[t], xa[t])
+        b = graphed.step(x[t], xa[t]) if t < 2 else graphed.step_graphed(x[t], xa[t])
+        assert int(b.pred) == a.pred
+        assert torch.equal(a.final_logits, b.final_logits) and torch.equal(a.dota_logits, b.dota_logits)
+    assert graphed._graph is not None and graphed.fits == eager.fits == 2 * T
+    assert torch.equal(eager.ops.cache.mu, graphed.ops.cache.mu) and torch.equal(eager.ops.cache.c, graphed.ops.cache.c)

@@ -13,7 +13,11 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 cfg = {'epsilon': 1e-4, 'sigma': 1e-4, 'eta': 0.1, 'rho': 0.02}
-K, M, D, T = 1156, 8, 1024, 6
+K, M, D, T = 1156, 8, 1024, 12
+# UA_SHARDED_GRAPH=1: steps >= 3 replay the CUDA graph of the step with the NCCL all-gather captured in it. Off by default:
+# the one attempt on 2 x B200 (torch 2.11, NCCL 2.28.9) did not return within 300 s and was not debugged further; the
+# graph replay itself is covered on one GPU (tests/test_gpu_adapters.py::test_class_sharded_step_as_cuda_graph).
+GRAPH_FROM = 3 if os.environ.get("UA_SHARDED_GRAPH") == "1" else T
 text = torch.from_numpy(synth.unit_rows(K, D, 7)).to(dev)
 x, xa, _ = synth.features(T, 1, D, text.cpu().numpy(), 8)       # same on every rank (replicated encoder output)
 x, xa = torch.from_numpy(x * 2.5).float().to(dev), torch.from_numpy(xa * 1.5).float().to(dev)
@@ -25,25 +29,27 @@ for t in range(T):
     torch.cuda.synchronize(); dist.barrier()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
-    out = shard.step(x[t], xa[t])
+    out = shard.step(x[t], xa[t]) if t < GRAPH_FROM else shard.step_graphed(x[t], xa[t])
     e.record(); torch.cuda.synchronize()
     times.append(s.elapsed_time(e))
     feats, clip_logits, _, prob, _ = ua.zero_shot_head(x[t], text)
     dl = full.predict_then_fit(feats.mean(0, keepdim=True).half(), feats, prob)
     full.fit(ua.zero_shot_head(xa[t], text)[0], prob)
     final, arg, _ = ua.fuse_logits(clip_logits, dl, full.c, cfg['rho'], cfg['eta'], 1, 'mode_dota')
-    ok &= out.pred == int(arg[0])
+    ok &= int(out.pred) == int(arg[0])
     ok &= torch.allclose(out.clip_logits, clip_logits, rtol=1e-6, atol=1e-6)
     ok &= torch.allclose(out.dota_logits, dl, rtol=1e-6, atol=1e-4)
     ok &= torch.allclose(out.final_logits, final, rtol=1e-5, atol=1e-4)
 ok &= torch.equal(shard.ops.cache.mu[0], full.mu[shard.k_lo:shard.k_hi])
 ok &= torch.equal(shard.ops.cache.var[0], full.var[shard.k_lo:shard.k_hi])
-tmax = torch.tensor([sum(times[2:]) / len(times[2:])], device=dev)
+eager_t, graph_t = times[1:GRAPH_FROM], times[GRAPH_FROM + 1:]
+tmax = torch.tensor([sum(eager_t) / len(eager_t), sorted(graph_t)[len(graph_t) // 2] if graph_t else float("nan")], device=dev)
 dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
     print(json.dumps({"check": "class_sharded_modedota_nccl", "world": world, "classes_per_rank": shard.k_hi - shard.k_lo,
-                      "all_ranks_match_unsharded": bool(flag.item()), "sharded_step_ms_max_over_ranks": round(float(tmax), 4)}))
+                      "all_ranks_match_unsharded": bool(flag.item()), "sharded_step_ms_max_over_ranks": round(float(tmax[0]), 4),
+                      "graphed_step_ms_max_over_ranks": None if GRAPH_FROM >= T else round(float(tmax[1]), 4)}))
 dist.destroy_process_group()
 sys.exit(0 if flag.item() else 1)

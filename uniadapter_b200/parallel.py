@@ -126,8 +126,12 @@ class CudaShardOps:
         _lib.check(rc, "ua_modedota_step_f32")
 
     def fuse(self, clip, dota, c_sum, c_count, rho, eta, batch):
+        """c_sum: the closed-form sum of the soft counts, a float or a 1-element device tensor (CUDA-graph safe)."""
         from .fusion import fuse_logits
-        final, arg, _ = fuse_logits(clip, dota, None, rho, eta, batch, 'mode_dota', c_sum=c_sum, c_count=c_count)
+        if torch.is_tensor(c_sum):
+            final, arg, _ = fuse_logits(clip, dota, c_sum.view(1), rho, eta, batch, 'mode_dota', c_count=c_count)
+        else:
+            final, arg, _ = fuse_logits(clip, dota, None, rho, eta, batch, 'mode_dota', c_sum=c_sum, c_count=c_count)
         return final, arg
 
     def softmax(self, logits):
@@ -165,6 +169,7 @@ class ShardedModeDota:
         self.send = self.ops.empty(2, self.K_pad)
         self.scratch_row = self.ops.empty(self.K_pad)
         self.recv = self.ops.empty(self.world, 2, self.K_pad)
+        self._graph = None
 
     def _all_gather(self):
         if self.gather_fn is not None:
@@ -198,8 +203,9 @@ class ShardedModeDota:
         x_pred = self._x.mean(0, keepdim=True).half().float()           # Uni_Adapter.py:416
         ops.predict_local(x_pred, self.send[1])                         # local cache logits -> send[1]
 
-    def finish(self, feats_aug_raw):
-        """Phase 2 (after the exchange): replicated softmax / fusion, local fits."""
+    def finish(self, feats_aug_raw, device_counts=None):
+        """Phase 2 (after the exchange): replicated softmax / fusion, local fits. ``device_counts``: 1-element device
+        tensor holding sum(c) (advanced on the device, for CUDA-graph replay); the prediction then stays a tensor."""
         cfg, ops, x = self.cfg, self.ops, self._x
         clip, dota = self.assemble(self.recv)
         prob = ops.softmax(clip)
@@ -209,6 +215,36 @@ class ShardedModeDota:
             x_aug = ops.head_local(feats_aug_raw, self.scratch_row)     # only its xnorm is used
             ops.fit(x_aug, prob, self.k_lo)                             # augmented view, original prob_map (:430)
             self.fits += 1
+        if device_counts is not None:
+            device_counts.add_(float(x.shape[0] * (2 if feats_aug_raw is not None else 1)))
+            final, arg = ops.fuse(clip, dota, device_counts, self.K * self.M, cfg['rho'], cfg['eta'], x.shape[0])
+            return ShardedStepOutput(final, arg, clip, dota)
         c_sum = closed_form_count_sum(self.K, self.fits, x.shape[0])
         final, arg = ops.fuse(clip, dota, c_sum, self.K * self.M, cfg['rho'], cfg['eta'], x.shape[0])
         return ShardedStepOutput(final, int(arg[0]), clip, dota)
+
+    def step_graphed(self, feats_raw: torch.Tensor, feats_aug_raw: torch.Tensor) -> ShardedStepOutput:
+        """The same step as one CUDA-graph replay (the NCCL all-gather is captured with it): no host work between the
+        ~15 launches of a step, which is what bounds the eager step (0.3 ms for a 33 us cache pass). Call after at
+        least one eager ``step`` (communicator warm-up). Verified on one GPU (world 1 and emulated ranks); with a real
+        NCCL group the captured all-gather did not complete in the one 2-GPU attempt of round 1 (tools/check_sharded_nccl.py,
+        UA_SHARDED_GRAPH=1) -- the planned replacement is a peer-memory exchange kernel inside the same graph. ``pred`` of the result is a 1-element device tensor; inputs are
+        copied into static buffers, outputs are static buffers overwritten by the next replay."""
+        if self._graph is None:
+            self._g_in = feats_raw.clone().contiguous()
+            self._g_aug = feats_aug_raw.clone().contiguous()
+            # sum(c) so far in closed form (H7): K initial counts + one per fitted row
+            self._g_counts = torch.full((1,), closed_form_count_sum(self.K, self.fits, feats_raw.shape[0]),
+                                        dtype=torch.float32, device=feats_raw.device)
+            self._graph = torch.cuda.CUDAGraph()
+            fits_before = self.fits
+            with torch.cuda.graph(self._graph):
+                self.local_logits(self._g_in)
+                self._all_gather()
+                self._g_out = self.finish(self._g_aug, device_counts=self._g_counts)
+            self.fits = fits_before       # capture runs no kernel: the counters advance on replay
+        self._g_in.copy_(feats_raw)
+        self._g_aug.copy_(feats_aug_raw)
+        self._graph.replay()
+        self.fits += 2
+        return self._g_out
