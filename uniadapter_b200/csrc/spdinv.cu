@@ -35,32 +35,54 @@ __device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Correctly-rounded reciprocal of a normal positive float (MUFU.RCP + one Newton step in FMA): the same value as
+// 1.0f / v without the range checks and slow path of the division sequence.
+__device__ __forceinline__ float rcp_rn_pos(float v) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  const float e = -fmaf(v, r, -1.0f);
+  return fmaf(r, e, r);
+}
+
 // Inverse of a 16x16 SPD block by one warp: lane owns row (lane>>1), columns 8*(lane&1) .. +7. Unpivoted scalar
-// Gauss-Jordan, fully unrolled so every register index is static. Result written to Ps (row-major 16x16).
+// Gauss-Jordan, fully unrolled so every register index is static. The chain of 16 dependent pivots is the serial core
+// of the whole inversion (28 % of the kernel's stall samples), so the NEXT pivot's reciprocal is computed one step
+// ahead from three extra shuffles of the pre-update state: a'[t+1][t+1] = fma(-a[t+1][t], a[t][t+1] * p, a[t+1][t+1])
+// is bit-identical to what the update below writes, and the per-pivot chain shrinks from shuffle -> divide -> shuffle ->
+// multiply -> fma to multiply -> fma -> reciprocal. Result written to Ps (row-major 16x16).
 __device__ __forceinline__ void invert16_warp(const float* __restrict__ Akk /* smem 16x16 */, float* __restrict__ Ps,
                                               int lane) {
   const int i = lane >> 1, h = lane & 1;
   float a[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) a[j] = Akk[i * kNB + h * 8 + j];
+  float p = rcp_rn_pos(__shfl_sync(kFullMask, a[0], 0));
 #pragma unroll
   for (int t = 0; t < kNB; ++t) {
     // pivot row t lives in lanes 2t (cols 0-7) and 2t+1 (cols 8-15); column t lives in register t&7 of half t>>3
-    const float att = __shfl_sync(kFullMask, a[t & 7], 2 * t + (t >> 3));
-    const float p = 1.0f / att;
     const float cit = __shfl_sync(kFullMask, a[t & 7], (lane & ~1) | (t >> 3));  // a[i][t]
     float row[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) row[j] = __shfl_sync(kFullMask, a[j], 2 * t + h) * p;  // a[t][j] * p
+    for (int j = 0; j < 8; ++j) row[j] = __shfl_sync(kFullMask, a[j], 2 * t + h);  // a[t][j]
+    float pnext = 0.f;
+    if (t + 1 < kNB) {
+      const int u = t + 1;
+      const float a11 = __shfl_sync(kFullMask, a[u & 7], 2 * u + (u >> 3));
+      const float a10 = __shfl_sync(kFullMask, a[t & 7], 2 * u + (t >> 3));
+      const float a01 = __shfl_sync(kFullMask, a[u & 7], 2 * t + (u >> 3));
+      pnext = rcp_rn_pos(fmaf(-a10, a01 * p, a11));
+    }
     const bool prow = (i == t);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const bool pcol = (h * 8 + j == t);
+      const float rp = row[j] * p;
       float v;
-      if (prow) v = pcol ? p : row[j];
-      else v = pcol ? -cit * p : fmaf(-cit, row[j], a[j]);
+      if (prow) v = pcol ? p : rp;
+      else v = pcol ? -cit * p : fmaf(-cit, rp, a[j]);
       a[j] = v;
     }
+    p = pnext;
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) Ps[i * kNB + h * 8 + j] = a[j];
