@@ -172,7 +172,7 @@ def test_tensor_core_head_vs_reference_golden(cuda_device):
     np.testing.assert_array_equal(arg.cpu().numpy(), gold["pred"])
 
 
-@pytest.mark.parametrize("shape", [(1, 128, 1), (2, 130, 2), (3, 513, 6), (2, 700, 4)])
+@pytest.mark.parametrize("shape", [(1, 128, 1), (2, 130, 2), (3, 513, 6), (2, 700, 4), (2, 2, 1), (1, 257, 3)])
 def test_tensor_core_attention_vs_sdpa_float64(shape, cuda_device):
     """csrc/attention.cu (3xTF32, P in tensor memory, base-2 online softmax) vs torch SDPA evaluated in float64."""
     import torch.nn.functional as F

@@ -472,7 +472,10 @@ extern "C" int ua_attention_f32(const float* q_hi, const float* q_lo, const floa
     return UA_ERR_CUDA;
   }
   // One CTA per 128 query rows. (Handing the one leftover row of 512 + 1 tokens to a SIMT side kernel, so that every
-  // (batch, head) needs 4 CTAs instead of 5, was tried: the latency-bound side kernel cost what the saved wave gained.)
+  // (batch, head) needs 4 CTAs instead of 5, was tried: the latency-bound side kernel cost what the saved wave gained.
+  // So was a SIMT branch for the leftover row INSIDE this kernel: one row still has to read the (batch, head)'s whole K
+  // and V^T, 540 KB through one SM's L2 port = 14 us at best against 26 us for the tensor-core CTA, and the plain
+  // version measured 100 us per tail CTA: attention 159 -> 250 us per launch. Removed.)
   const int q_tiles = (N + kQ - 1) / kQ;
   dim3 grid(q_tiles, BH);
   attention_kernel<<<grid, kAttnThreads, AttnSmem::kTotal, (cudaStream_t)stream>>>(mq_hi, mq_lo, mk_hi, mk_lo, mv_hi,
