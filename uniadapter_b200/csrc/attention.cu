@@ -137,36 +137,52 @@ __device__ __forceinline__ float a_tf32(float x) {
 }
 
 // ---- operand preparation -----------------------------------------------------------------------------------------
-// 1-D grid of B*H*(Npad/32) slabs, block 256: a 32-token slab of one head. Q (scaled), K: straight (hi, lo) copies;
-// V: transposed through shared memory so that kv becomes the contiguous dimension.
+// 1-D grid of B*H*ceil(Npad/64) slabs, block 256: a 64-token slab of one head, 16-byte accesses throughout.
+// Q (scaled), K: straight (hi, lo) copies; V: transposed through shared memory so that kv becomes the contiguous
+// dimension (256-byte runs per head-dimension row).
+constexpr int kPrepTokens = 64;
+
 __global__ void __launch_bounds__(256)
     attn_prepare_kernel(const float* __restrict__ qkv, int B, int N, int H, int Npad, float* __restrict__ q_hi,
                         float* __restrict__ q_lo, float* __restrict__ k_hi, float* __restrict__ k_lo,
                         float* __restrict__ vt_hi, float* __restrict__ vt_lo) {
-  __shared__ float s_v[32][kHd + 1];
-  const int nslab = Npad / 32;
+  __shared__ float s_v[kPrepTokens][kHd + 1];
+  const int nslab = (Npad + kPrepTokens - 1) / kPrepTokens;
   const int bh = (int)blockIdx.x / nslab, b = bh / H, h = bh - b * H;
-  const int n0 = ((int)blockIdx.x - bh * nslab) * 32;
+  const int n0 = ((int)blockIdx.x - bh * nslab) * kPrepTokens;
   const int C3 = 3 * H * kHd;
-  for (int e = threadIdx.x; e < 32 * kHd; e += 256) {
-    const int r = e / kHd, d = e - r * kHd, n = n0 + r;
-    float q = 0.f, k = 0.f, v = 0.f;
+  auto split4 = [](const float4 x, float4& hi, float4& lo) {
+    hi.x = a_tf32(x.x), hi.y = a_tf32(x.y), hi.z = a_tf32(x.z), hi.w = a_tf32(x.w);
+    lo.x = x.x - hi.x, lo.y = x.y - hi.y, lo.z = x.z - hi.z, lo.w = x.w - hi.w;
+  };
+  for (int e = threadIdx.x; e < kPrepTokens * (kHd / 4); e += 256) {
+    const int r = e / (kHd / 4), d = (e - r * (kHd / 4)) * 4, n = n0 + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (n < N) {
       const float* row = qkv + ((size_t)b * N + n) * C3 + h * kHd + d;
-      q = __ldg(row) * kQScale, k = __ldg(row + H * kHd), v = __ldg(row + 2 * H * kHd);
+      float4 q = __ldg(reinterpret_cast<const float4*>(row));
+      const float4 k = __ldg(reinterpret_cast<const float4*>(row + H * kHd));
+      v = __ldg(reinterpret_cast<const float4*>(row + 2 * H * kHd));
+      q.x *= kQScale, q.y *= kQScale, q.z *= kQScale, q.w *= kQScale;
       const size_t o = ((size_t)bh * N + n) * kHd + d;
-      const float qh = a_tf32(q), kh = a_tf32(k);
-      q_hi[o] = qh, q_lo[o] = q - qh, k_hi[o] = kh, k_lo[o] = k - kh;
+      float4 hi, lo;
+      split4(q, hi, lo);
+      *reinterpret_cast<float4*>(q_hi + o) = hi, *reinterpret_cast<float4*>(q_lo + o) = lo;
+      split4(k, hi, lo);
+      *reinterpret_cast<float4*>(k_hi + o) = hi, *reinterpret_cast<float4*>(k_lo + o) = lo;
     }
-    s_v[r][d] = v;
+    s_v[r][d] = v.x, s_v[r][d + 1] = v.y, s_v[r][d + 2] = v.z, s_v[r][d + 3] = v.w;
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < 32 * kHd; e += 256) {
-    const int d = e / 32, r = e - d * 32;
-    const float v = s_v[r][d];
-    const float vh = a_tf32(v);
-    const size_t o = ((size_t)bh * kHd + d) * Npad + n0 + r;
-    vt_hi[o] = vh, vt_lo[o] = v - vh;
+  for (int e = threadIdx.x; e < kHd * (kPrepTokens / 4); e += 256) {
+    const int d = e / (kPrepTokens / 4), r = (e - d * (kPrepTokens / 4)) * 4;
+    if (n0 + r < Npad) {                     // Npad is a multiple of 32: whole float4 groups are inside or outside
+      const float4 v = make_float4(s_v[r][d], s_v[r + 1][d], s_v[r + 2][d], s_v[r + 3][d]);
+      float4 hi, lo;
+      split4(v, hi, lo);
+      const size_t o = ((size_t)bh * kHd + d) * Npad + n0 + r;
+      *reinterpret_cast<float4*>(vt_hi + o) = hi, *reinterpret_cast<float4*>(vt_lo + o) = lo;
+    }
   }
 }
 
@@ -442,7 +458,9 @@ extern "C" int ua_attn_prepare_f32(const float* qkv, int B, int N, int H, float*
   UA_REQUIRE(B >= 1 && N >= 1 && H >= 1 && (long long)B * H <= 65535, "ua_attn_prepare_f32: bad sizes B=%d N=%d H=%d", B,
              N, H);
   const int Npad = (int)ua_attn_padded_tokens(N);
-  const unsigned grid = (unsigned)((long long)B * H * (Npad / 32));
+  UA_REQUIRE(((uintptr_t)qkv | (uintptr_t)q_hi | (uintptr_t)q_lo | (uintptr_t)k_hi | (uintptr_t)k_lo | (uintptr_t)vt_hi |
+              (uintptr_t)vt_lo) % 16 == 0, "ua_attn_prepare_f32: pointers must be 16-byte aligned");
+  const unsigned grid = (unsigned)((long long)B * H * ((Npad + kPrepTokens - 1) / kPrepTokens));
   attn_prepare_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(qkv, B, N, H, Npad, q_hi, q_lo, k_hi, k_lo, vt_hi, vt_lo);
   return check_launch("ua_attn_prepare_f32");
 }
