@@ -396,11 +396,22 @@ template <int C>
 __global__ void __launch_bounds__(256) pointwise_linear_split_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                    const float* __restrict__ b, int relu, long long M,
                                                                    int N, float* __restrict__ hi, float* __restrict__ lo) {
+  // A thread keeps its 4 output channels (weights + bias in registers) and walks rows: per row three broadcast loads,
+  // 4*C FMAs and two 16-byte stores, so the kernel is the HBM write stream of the (hi, lo) pair (8*N bytes per row).
   const int n4 = N / 4;
-  const long long total = M * n4;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const long long row = e / n4;
-    const int c0 = (int)(e - row * n4) * 4;
+  const long long tglobal = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long tstride = (long long)gridDim.x * blockDim.x;     // a multiple of n4 (host guarantees it)
+  const int c0 = (int)(tglobal % n4) * 4;
+  float wr[4][C], br[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    br[j] = __ldg(b + c0 + j);
+#pragma unroll
+    for (int c = 0; c < C; ++c) wr[j][c] = __ldg(w + (size_t)(c0 + j) * C + c);
+  }
+  const long long row_stride = tstride / n4;
+#pragma unroll 2
+  for (long long row = tglobal / n4; row < M; row += row_stride) {
     float xin[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) xin[c] = __ldg(x + row * C + c);
@@ -409,8 +420,8 @@ __global__ void __launch_bounds__(256) pointwise_linear_split_kernel(const float
     for (int j = 0; j < 4; ++j) {
       float acc = 0.f;
 #pragma unroll
-      for (int c = 0; c < C; ++c) acc = fmaf(xin[c], __ldg(w + (size_t)(c0 + j) * C + c), acc);
-      acc += __ldg(b + c0 + j);
+      for (int c = 0; c < C; ++c) acc = fmaf(xin[c], wr[j][c], acc);
+      acc += br[j];
       o[j] = relu ? fmaxf(acc, 0.f) : acc;
     }
     float4 h, l;
@@ -418,8 +429,8 @@ __global__ void __launch_bounds__(256) pointwise_linear_split_kernel(const float
     h.y = tf32_round(o[1]), l.y = o[1] - h.y;
     h.z = tf32_round(o[2]), l.z = o[2] - h.z;
     h.w = tf32_round(o[3]), l.w = o[3] - h.w;
-    *reinterpret_cast<float4*>(hi + row * N + c0) = h;
-    *reinterpret_cast<float4*>(lo + row * N + c0) = l;
+    __stcs(reinterpret_cast<float4*>(hi + row * N + c0), h);
+    __stcs(reinterpret_cast<float4*>(lo + row * N + c0), l);
   }
 }
 
@@ -580,6 +591,9 @@ extern "C" int ua_pointwise_linear_split_f32(const float* x, const float* w, con
   const long long total = M * (N / 4);
   long long blocks = (total + 255) / 256;
   if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  // the kernel keeps a thread on fixed output channels: the grid size in threads must be a multiple of N/4
+  UA_UNSUPPORTED(256 % (N / 4) != 0 && (N / 4) % 256 != 0, "ua_pointwise_linear_split_f32: N=%d (N/4 must divide 256 or be a multiple of it)", N);
+  if ((N / 4) > 256) blocks = (blocks + (N / 4) / 256 - 1) / ((N / 4) / 256) * ((N / 4) / 256);
   cudaStream_t st = (cudaStream_t)stream;
   if (C == 3)
     pointwise_linear_split_kernel<3><<<(unsigned)blocks, 256, 0, st>>>(x, w, b, relu, M, N, out_hi, out_lo);
