@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
   unsigned char* s_v = s_k + L::kKBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_v + L::kVBytes);
   uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = bars + 2, *v_full = bars + 3, *v_empty = bars + 4,
-           *s_full = bars + 5, *s_free = bars + 6, *p_ready = bars + 7, *o_done = bars + 8;
+           *s_full = bars + 5 /* [2]: one per S buffer */, *p_ready = bars + 7, *o_done = bars + 8;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
 
   if (warp == 0 && a_elect_one()) {
     mbar_init(q_full, 1), mbar_init(k_full, 1), mbar_init(k_empty, 1), mbar_init(v_full, 1), mbar_init(v_empty, 1);
-    mbar_init(s_full, 1), mbar_init(s_free, 4), mbar_init(p_ready, 4), mbar_init(o_done, 1);
+    mbar_init(s_full, 1), mbar_init(s_full + 1, 1), mbar_init(p_ready, 4), mbar_init(o_done, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -234,7 +234,10 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
   __syncthreads();
   a_fence_after();
   const uint32_t tmem = *s_tmem;
-  const uint32_t t_s = tmem, t_phi = tmem + 128, t_plo = tmem + 256, t_o = tmem + 384;
+  // S is double-buffered (columns 0-127 / 128-255) and P_hi is written IN PLACE over the S block it came from, so that
+  // S_{j+1} = Q K_{j+1}^T runs on the tensor pipe while the softmax warps work on block j (before: S, softmax and PV of a
+  // block ran strictly one after the other, tensor pipe 30 % active). P_lo 256-383, O 384-447.
+  const uint32_t t_s = tmem, t_plo = tmem + 256, t_o = tmem + 384;
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -268,14 +271,15 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
       const uint32_t id_s = a_idesc(kQ, kKv), id_o = a_idesc(kQ, kHd);
       const uint32_t q_base = smem_u32(s_q), k_base = smem_u32(s_k), v_base = smem_u32(s_v);
       mbar_wait(q_full, 0);
-      for (int j = 0; j < nkv; ++j) {
-        const uint32_t ph = (uint32_t)j & 1u;
-        mbar_wait(k_full, ph);
-        if (j > 0) mbar_wait(s_free, ph ^ 1u);       // the softmax warps have read S_{j-1}
+      // S_j = Q K_j^T into S buffer j & 1: 2 k-blocks x 4 k-steps x 3 products; a short last block only computes the
+      // columns it has. In-order execution of the MMAs of this thread is what makes the buffer reuse safe: S_{j+1}
+      // overwrites the buffer of block j-1 and is issued after PV_{j-1}, the last reader of P_hi_{j-1}.
+      auto issue_s = [&](int j) {
+        mbar_wait(k_full, (uint32_t)j & 1u);
         a_fence_after();
-        // S_j = Q K_j^T: 2 k-blocks x 4 k-steps x 3 products; a short last block only computes the columns it has
         const int kv_valid = min(kKv, p.N - j * kKv);
         const uint32_t id_sj = kv_valid == kKv ? id_s : a_idesc(kQ, (kv_valid + 15) & ~15);
+        const uint32_t t_sj = t_s + (uint32_t)(j & 1) * 128u;
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb) {
           const uint64_t qh = a_smem_desc(q_base + (2 * kb) * L::kTile), ql = a_smem_desc(q_base + (2 * kb + 1) * L::kTile);
@@ -283,14 +287,21 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint64_t off = (uint64_t)(ks * 2);
-            a_umma_ss(t_s, ql + off, kh + off, id_sj, (kb | ks) != 0);
-            a_umma_ss(t_s, qh + off, kl + off, id_sj, 1u);
-            a_umma_ss(t_s, qh + off, kh + off, id_sj, 1u);
+            a_umma_ss(t_sj, ql + off, kh + off, id_sj, (kb | ks) != 0);
+            a_umma_ss(t_sj, qh + off, kl + off, id_sj, 1u);
+            a_umma_ss(t_sj, qh + off, kh + off, id_sj, 1u);
           }
         }
         a_commit(k_empty);
-        a_commit(s_full);
+        a_commit(s_full + (j & 1));
+      };
+      issue_s(0);
+      for (int j = 0; j < nkv; ++j) {
+        const uint32_t ph = (uint32_t)j & 1u;
+        if (j + 1 < nkv) issue_s(j + 1);             // runs while the softmax warps are busy with block j
         // O += P_j V_j once P_j is in tensor memory: 4 k-blocks x 4 k-steps x 3 products, A from TMEM
+        const int kv_valid = min(kKv, p.N - j * kKv);
+        const uint32_t t_phi = t_s + ph * 128u;
         mbar_wait(v_full, ph);
         mbar_wait(p_ready, ph);
         a_fence_after();
@@ -322,7 +333,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
     for (int j = 0; j < nkv; ++j) {
       const uint32_t ph = (uint32_t)j & 1u;
       const int kv_valid = min(kKv, p.N - j * kKv);    // columns beyond the sequence are masked
-      mbar_wait(s_full, ph);
+      const uint32_t t_sj = t_s + ph * 128u;           // S_j, and P_hi_j in place once pass 2 has rewritten it
+      mbar_wait(s_full + (j & 1), (uint32_t)(j >> 1) & 1u);
       a_fence_after();
       // pass 1: row maximum of the block (columns beyond the sequence count as -inf; branch-free so that the 32
       // per-column chains of a thread interleave)
@@ -331,7 +343,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
       for (int c0 = 0; c0 < kKv; c0 += 32) {
         if (c0 >= kv_valid) break;
         float v[32];
-        a_tmem_ld32(t_s + lane_off + (uint32_t)c0, v);
+        a_tmem_ld32(t_sj + lane_off + (uint32_t)c0, v);
         const int nv = kv_valid - c0;
 #pragma unroll
         for (int i = 0; i < 32; ++i) bmax = fmaxf(bmax, i < nv ? v[i] : -INFINITY);
@@ -358,7 +370,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
         if (c0 >= kv_valid) break;                     // the PV MMAs stop at ceil(kv_valid / 8) * 8 columns
         float v[32], hi[32];
         if (c0 < kv_valid) {
-          a_tmem_ld32(t_s + lane_off + (uint32_t)c0, v);
+          a_tmem_ld32(t_sj + lane_off + (uint32_t)c0, v);
           const int nv = kv_valid - c0;
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
@@ -371,7 +383,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
 #pragma unroll
           for (int i = 0; i < 32; ++i) hi[i] = 0.f, v[i] = 0.f;
         }
-        a_tmem_st32(t_phi + lane_off + (uint32_t)c0, hi);
+        a_tmem_st32(t_sj + lane_off + (uint32_t)c0, hi);     // in place: this thread's row, columns it has just read
         a_tmem_st32(t_plo + lane_off + (uint32_t)c0, v);
       }
       a_tmem_st_wait();
@@ -379,10 +391,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
       m_run = m_new;
       a_fence_before();
       __syncwarp();
-      if (lane == 0) {
-        a_mbar_arrive(s_free);      // S_j has been consumed
-        a_mbar_arrive(p_ready);     // P_j (and the rescaled O) are in tensor memory
-      }
+      if (lane == 0) a_mbar_arrive(p_ready);     // P_j (and the rescaled O) are in tensor memory
     }
     // epilogue: O / l as the (hi, lo) pair of the projection GEMM's A operand
     mbar_wait(o_done, (uint32_t)(nkv - 1) & 1u);
