@@ -96,6 +96,28 @@ __device__ __forceinline__ void a_tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+// tcgen05.ld without the wait, and a wait that is tied to the destination registers (so that no use of them can be
+// scheduled above it): two 32-column loads can be in flight before the first value is consumed.
+__device__ __forceinline__ void a_tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void a_tmem_ld_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
 __device__ __forceinline__ void a_tmem_st32(uint32_t taddr, const float (&v)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -340,13 +362,32 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
       // per-column chains of a thread interleave)
       float bmax = -INFINITY;
 #pragma unroll 1
-      for (int c0 = 0; c0 < kKv; c0 += 32) {
+      for (int c0 = 0; c0 < kKv; c0 += 64) {           // two 32-column loads in flight per round trip
         if (c0 >= kv_valid) break;
-        float v[32];
-        a_tmem_ld32(t_sj + lane_off + (uint32_t)c0, v);
-        const int nv = kv_valid - c0;
+        uint32_t ra[32], rb[32];
+        const bool two = c0 + 32 < kv_valid;
+        a_tmem_ld32_issue(t_sj + lane_off + (uint32_t)c0, ra);
+        if (two) a_tmem_ld32_issue(t_sj + lane_off + (uint32_t)(c0 + 32), rb);
+        a_tmem_ld_wait(ra);
+        const int na = kv_valid - c0;
+        if (na >= 32) {                                // full chunk (warp-uniform): no masking selects
 #pragma unroll
-        for (int i = 0; i < 32; ++i) bmax = fmaxf(bmax, i < nv ? v[i] : -INFINITY);
+          for (int i = 0; i < 32; ++i) bmax = fmaxf(bmax, __uint_as_float(ra[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) bmax = fmaxf(bmax, i < na ? __uint_as_float(ra[i]) : -INFINITY);
+        }
+        if (two) {
+          a_tmem_ld_wait(rb);
+          const int nb = na - 32;
+          if (nb >= 32) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) bmax = fmaxf(bmax, __uint_as_float(rb[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) bmax = fmaxf(bmax, i < nb ? __uint_as_float(rb[i]) : -INFINITY);
+          }
+        }
       }
       const float m_new = fmaxf(m_run, bmax);
       const float alpha = a_exp2(m_run - m_new);       // 0 at the first block (m_run = -inf)
@@ -365,26 +406,45 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
       }
       // pass 2: P = 2^(S - m_new) as a (hi, lo) pair into tensor memory, running sum
       float psum = 0.f;
-#pragma unroll 1
-      for (int c0 = 0; c0 < kKv; c0 += 32) {
-        if (c0 >= kv_valid) break;                     // the PV MMAs stop at ceil(kv_valid / 8) * 8 columns
-        float v[32], hi[32];
-        if (c0 < kv_valid) {
-          a_tmem_ld32(t_sj + lane_off + (uint32_t)c0, v);
-          const int nv = kv_valid - c0;
+      auto weights = [&](uint32_t (&r)[32], int c0) {  // one 32-column chunk: P = 2^(S - m), split, store in place / P_lo
+        float hi[32], lo[32];
+        const int nv = kv_valid - c0;
+        // (hi, lo) split of a weight by TRUNCATION (one LOP3 instead of a cvt.rna on the conversion pipe, which the
+        // MUFU.EX2 of the same weight already loads): hi keeps 10 mantissa bits, lo = e - hi is exact (13 bits); the
+        // tensor core truncates lo to tf32 itself, leaving 2^-21 relative per weight instead of 2^-22
+        if (nv >= 32) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const float e = a_exp2((i < nv ? v[i] : -INFINITY) - m_new);
+            const float e = a_exp2(__uint_as_float(r[i]) - m_new);
             psum += e;
-            hi[i] = a_tf32(e);
-            v[i] = e - hi[i];
+            hi[i] = __uint_as_float(__float_as_uint(e) & 0xffffe000u);
+            lo[i] = e - hi[i];
           }
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) hi[i] = 0.f, v[i] = 0.f;
+          for (int i = 0; i < 32; ++i) {
+            const float e = a_exp2((i < nv ? __uint_as_float(r[i]) : -INFINITY) - m_new);
+            psum += e;
+            hi[i] = __uint_as_float(__float_as_uint(e) & 0xffffe000u);
+            lo[i] = e - hi[i];
+          }
         }
         a_tmem_st32(t_sj + lane_off + (uint32_t)c0, hi);     // in place: this thread's row, columns it has just read
-        a_tmem_st32(t_plo + lane_off + (uint32_t)c0, v);
+        a_tmem_st32(t_plo + lane_off + (uint32_t)c0, lo);
+      };
+#pragma unroll 1
+      for (int c0 = 0; c0 < kKv; c0 += 64) {
+        if (c0 >= kv_valid) break;                     // the PV MMAs stop at ceil(kv_valid / 8) * 8 columns
+        uint32_t ra[32], rb[32];
+        const bool two = c0 + 32 < kv_valid;
+        a_tmem_ld32_issue(t_sj + lane_off + (uint32_t)c0, ra);
+        if (two) a_tmem_ld32_issue(t_sj + lane_off + (uint32_t)(c0 + 32), rb);
+        a_tmem_ld_wait(ra);
+        weights(ra, c0);
+        if (two) {
+          a_tmem_ld_wait(rb);
+          weights(rb, c0 + 32);
+        }
       }
       a_tmem_st_wait();
       l_run = l_run * alpha + psum;
