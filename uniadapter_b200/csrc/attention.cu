@@ -262,8 +262,12 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
   const uint32_t t_s = tmem, t_plo = tmem + 256, t_o = tmem + 384;
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (a_elect_one()) {
+    // ===== TMA producers: lane 0 streams Q and K, lane 1 streams V^T =====
+    // Two lanes because the two streams wait on different consumers: K_{j+1} may load as soon as S_j has been
+    // computed (early: S runs one block ahead of the softmax), V_{j+1} only when PV_j is done. A single producer
+    // thread that alternates between them holds K_{j+1} back behind the wait for PV_{j-1}, and the softmax warps then
+    // wait for S_{j+1} (22 % of the kernel's stall samples before the split).
+    if (lane == 0) {
       const int qrow = bh * p.N + q0;
       mbar_expect_tx(q_full, (uint32_t)L::kQBytes);
       for (int kb = 0; kb < 2; ++kb) {
@@ -279,6 +283,10 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
           a_tma_load_2d(s_k + (2 * kb) * L::kTile, &map_k_hi, k_full, kb * 32, krow);
           a_tma_load_2d(s_k + (2 * kb + 1) * L::kTile, &map_k_lo, k_full, kb * 32, krow);
         }
+      }
+    } else if (lane == 1) {
+      for (int j = 0; j < nkv; ++j) {
+        const uint32_t ph = (uint32_t)j & 1u;
         mbar_wait(v_empty, ph ^ 1u);
         mbar_expect_tx(v_full, (uint32_t)L::kVBytes);
         for (int kb = 0; kb < 4; ++kb) {
