@@ -566,6 +566,9 @@ extern "C" int ua_attention_f32(const float* q_hi, const float* q_lo, const floa
     set_error("ua_attention_f32: cudaFuncSetAttribute(%d B): %s", AttnSmem::kTotal, cudaGetErrorString(e));
     return UA_ERR_CUDA;
   }
+  // (A second softmax warpgroup -- 8 softmax warps, each thread one row and half of the columns, row maxima exchanged
+  // through shared memory -- was built and measured after the S double buffer: 123.5 us, no change. The per-block cycle
+  // is p_ready -> PV (tensor pipe) -> o_done -> rescale + pass 2 -> p_ready, not the exponentials.)
   // One CTA per 128 query rows. (Handing the one leftover row of 512 + 1 tokens to a SIMT side kernel, so that every
   // (batch, head) needs 4 CTAs instead of 5, was tried: the latency-bound side kernel cost what the saved wave gained.
   // So was a SIMT branch for the leftover row INSIDE this kernel: one row still has to read the (batch, head)'s whole K
