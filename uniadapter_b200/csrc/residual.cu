@@ -46,13 +46,17 @@ __device__ __forceinline__ float block_sum_256(float v, float* s_tmp) {
 // ---- constants of the cache that do not change during the 10 steps: log-determinant and log-weight per (k,m) ----
 __global__ void __launch_bounds__(kThreads)
     resid_prep_kernel(const float* __restrict__ var, const float* __restrict__ pi, int rows, int D, float eps,
-                      float* __restrict__ consts) {
+                      float* __restrict__ consts, float* __restrict__ inv) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const float* v = var + (size_t)row * D;
   float ld = 0.f;
-  for (int d = lane; d < D; d += 32) ld += logf(fmaxf(__fadd_rn(v[d], eps), 1e-8f));
+  for (int d = lane; d < D; d += 32) {
+    const float vv = fmaxf(__fadd_rn(v[d], eps), 1e-8f);
+    ld += logf(vv);
+    inv[(size_t)row * D + d] = __fdiv_rn(1.0f, vv);   // the cache does not change during the 10 steps: one division per
+  }                                                    // element and call instead of one per element and launch
   ld = warp_sum(ld);
   if (lane == 0) {
     consts[2 * row + 0] = ld;
@@ -139,7 +143,7 @@ __global__ void resid_bump_t_kernel(int* adam_t, int S, int iters) {
 struct FwdParams {
   const float* X;        // [S,K,D]
   const float* mu;       // [S,K,M,D]
-  const float* var;
+  const float* var;      // [S,K,M,D]: 1 / max(var + eps, 1e-8), precomputed once per call (resid_prep)
   const float* consts;   // [S,K,M,2]
   float* LM;             // [S,K,K]
   float* Wt;             // [S,K,K,M]: softmax over modes of lj (row i, class k)
@@ -161,12 +165,7 @@ __global__ void __launch_bounds__(kThreads, 3) resid_forward_kernel(const FwdPar
   const float* gvar = p.var + ((size_t)s * K + k0) * M * D;
   for (int idx = tid * 4; idx < ncols * D; idx += kThreads * 4) {
     const float4 m4 = __ldg(reinterpret_cast<const float4*>(gmu + idx));
-    const float4 v4 = __ldg(reinterpret_cast<const float4*>(gvar + idx));
-    float4 i4;
-    i4.x = __fdiv_rn(1.0f, fmaxf(__fadd_rn(v4.x, p.eps), 1e-8f));
-    i4.y = __fdiv_rn(1.0f, fmaxf(__fadd_rn(v4.y, p.eps), 1e-8f));
-    i4.z = __fdiv_rn(1.0f, fmaxf(__fadd_rn(v4.z, p.eps), 1e-8f));
-    i4.w = __fdiv_rn(1.0f, fmaxf(__fadd_rn(v4.w, p.eps), 1e-8f));
+    const float4 i4 = __ldg(reinterpret_cast<const float4*>(gvar + idx));     // 1 / v, precomputed by resid_prep
     *reinterpret_cast<float4*>(t_mu + idx) = m4;
     *reinterpret_cast<float4*>(t_iv + idx) = i4;
   }
@@ -341,7 +340,7 @@ __global__ void __launch_bounds__(kThreads, DBL == 1 ? 2 : 1) resid_backward_ker
   for (int idx = tid; idx < ncols * DB; idx += kThreads) {
     const int col = idx / DB, d = idx - col * DB;
     t_mu[idx] = __ldg(gmu + (size_t)col * D + d);
-    t_iv[idx] = __fdiv_rn(1.0f, fmaxf(__fadd_rn(__ldg(gvar + (size_t)col * D + d), p.eps), 1e-8f));
+    t_iv[idx] = __ldg(gvar + (size_t)col * D + d);          // 1 / v, precomputed by resid_prep
   }
   __syncthreads();
   const int nrg = (K + kBR - 1) / kBR;
@@ -399,7 +398,7 @@ struct Plan {
   int CB, nblk, DBL, NB;
   size_t smem_fwd, smem_loss, smem_bwd;
   // scratch offsets (floats)
-  size_t o_nrm, o_consts, o_lm, o_wt, o_dx, o_rdot, total;
+  size_t o_nrm, o_consts, o_lm, o_wt, o_dx, o_rdot, o_inv, total;
 };
 
 int make_plan(int S, int K, int M, int D, Plan& pl) {
@@ -447,6 +446,7 @@ int plan_aligned(int S, int K, int M, int D, Plan& pl) {
   pl.o_wt = o, o = align4(o + (size_t)S * K * K * M);
   pl.o_dx = o, o = align4(o + (size_t)S * K * D);
   pl.o_rdot = o, o = align4(o + (size_t)S * K * pl.NB);
+  pl.o_inv = o, o = align4(o + (size_t)S * K * M * D);
   pl.total = o;
   return UA_OK;
 }
@@ -469,7 +469,8 @@ struct Run {
 
 int launch_prep(const Run& r) {
   const int rows = r.S * r.K * r.M;
-  resid_prep_kernel<<<(rows + 7) / 8, kThreads, 0, r.st>>>(r.var, r.pi, rows, r.D, r.eps, r.scratch + r.pl.o_consts);
+  resid_prep_kernel<<<(rows + 7) / 8, kThreads, 0, r.st>>>(r.var, r.pi, rows, r.D, r.eps, r.scratch + r.pl.o_consts,
+                                                               r.scratch + r.pl.o_inv);
   return check_launch("resid_prep");
 }
 
@@ -483,7 +484,7 @@ int launch_embed(const Run& r, EmbedParams ep) {
 
 int launch_fwd_loss_bwd(const Run& r, float* out_loss, int loss_stride, int loss_index, bool backward) {
   FwdParams fp;
-  fp.X = r.X, fp.mu = r.mu, fp.var = r.var, fp.consts = r.scratch + r.pl.o_consts;
+  fp.X = r.X, fp.mu = r.mu, fp.var = r.scratch + r.pl.o_inv, fp.consts = r.scratch + r.pl.o_consts;
   fp.LM = r.scratch + r.pl.o_lm, fp.Wt = r.scratch + r.pl.o_wt;
   fp.K = r.K, fp.M = r.M, fp.D = r.D, fp.CB = r.pl.CB, fp.eps = r.eps;
   if (opt_in(resid_forward_kernel, r.pl.smem_fwd) != cudaSuccess) {
@@ -501,7 +502,7 @@ int launch_fwd_loss_bwd(const Run& r, float* out_loss, int loss_stride, int loss
   rc = check_launch("resid_loss");
   if (rc != UA_OK || !backward) return rc;
   BwdParams bp;
-  bp.X = r.X, bp.mu = r.mu, bp.var = r.var, bp.Wt = fp.Wt, bp.dX = r.scratch + r.pl.o_dx;
+  bp.X = r.X, bp.mu = r.mu, bp.var = r.scratch + r.pl.o_inv, bp.Wt = fp.Wt, bp.dX = r.scratch + r.pl.o_dx;
   bp.rdot = r.scratch + r.pl.o_rdot, bp.K = r.K, bp.M = r.M, bp.D = r.D, bp.NB = r.pl.NB, bp.eps = r.eps;
   cudaError_t e;
   if (r.pl.DBL == 2) {
