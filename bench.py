@@ -272,6 +272,8 @@ def run_ours(args):
     # ---- the HBM-bound kernel of the path at the size where it is HBM-bound (cfg 4: K=1156, M=8, D=1024) ----------
     lv = lvis_cache_roofline(dev, peak, flush)
     roofline["lvis_cache_step"] = lv
+    # ---- the tokenizer at the batch-64 shape of cfg 5 (the "FPS+kNN GB/s" part of BASELINE.json's metric) -------------
+    roofline["tokenizer_cfg5"] = tokenizer_sweep(dev, peak, flush)
 
     line = {"metric": METRIC, "value": round(value, 2), "unit": "clouds/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": round(ms_resident / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -329,6 +331,44 @@ def lvis_cache_roofline(dev, peak, flush):
             "achieved": round(by / us / 1e3, 1), "peak": peak, "unit": "GB/s", "frac": round(by / us / 1e3 / peak, 4),
             "traffic": LVIS_DRAM_TRAFFIC_BYTES,
             "plain_copy_same_bytes_us": round(copy_us, 2), "frac_of_plain_copy": round(copy_us / us, 4)}
+
+
+def tokenizer_sweep(dev, peak, flush):
+    """The tokenizer of BASELINE cfg 5 (Uni3D-L geometry: 64 clouds x 1024 xyz+rgb points, 512 groups x 64 neighbours):
+    FPS + kNN grouping as achieved GB/s over SURVEY 8d's algorithmic bytes (cloud in, centres + groups out). FPS is a
+    511-step dependent argmax chain per cloud (latency-bound by construction), so the fraction is reported, not a target."""
+    import uniadapter_b200 as ua
+    from uniadapter_b200.streams import unit_sphere_clouds
+    B, N, G, k = 64, 1024, 512, 64
+    g = torch.Generator().manual_seed(5)
+    xyz = unit_sphere_clouds(B, N, g).to(dev)
+    rgb = torch.rand(B, N, 3, generator=g).to(dev)
+    _, centers = ua.fps_sample(xyz, G, None)
+
+    def median_us(fn, n=9):
+        for _ in range(2):
+            fn()
+        ts = []
+        for _ in range(n):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn()
+            e.record()
+            torch.cuda.synchronize()
+            ts.append(s.elapsed_time(e) * 1e3)
+        return sorted(ts)[len(ts) // 2]
+
+    fps_us = median_us(lambda: ua.fps_sample(xyz, G, None))
+    knn_us = median_us(lambda: ua.knn_group(xyz, centers, k, rgb))
+    by = B * (N * 6 * 4 + G * 12 + G * k * 6 * 4)
+    tot = fps_us + knn_us
+    return {"workload": "cfg 5 tokenizer: 64 clouds x 1024 xyz+rgb points, 512 groups x 64 neighbours",
+            "kernels": "ua_fps_f32 (fps_reg_kernel) + ua_knn_group_f32 (knn_group_kernel)", "bound": "hbm",
+            "fps_us": round(fps_us, 1), "knn_group_us": round(knn_us, 1), "algorithmic_bytes": by,
+            "achieved": round(by / tot / 1e3, 1), "peak": peak, "unit": "GB/s", "frac": round(by / tot / 1e3 / peak, 4),
+            "clouds_per_s": round(B / tot * 1e6),
+            "note": "FPS is latency-bound (serial argmax chain, one CTA per cloud); kNN is issue-bound (selection)"}
 
 
 def main():
