@@ -443,3 +443,32 @@ def test_class_sharded_step_as_cuda_graph(cuda_device):
         assert torch.equal(a.final_logits, b.final_logits) and torch.equal(a.dota_logits, b.dota_logits)
     assert graphed._graph is not None and graphed.fits == eager.fits == 2 * T
     assert torch.equal(eager.ops.cache.mu, graphed.ops.cache.mu) and torch.equal(eager.ops.cache.c, graphed.ops.cache.c)
+
+
+@pytest.mark.parametrize("ksplit", [2, 4, 8])
+def test_dota_fit_class_split_over_a_cluster(ksplit, cuda_device):
+    """ua_dota_fit_f32 with the K classes split over the CTAs of a thread-block cluster (tuning knob dota_ksplit; the
+    partial class sums meet in rank 0 through distributed shared memory): Sigma, mu and c are bit-identical to the
+    unsplit launch, overall_Sigma differs only by the association of the class sum."""
+    import uniadapter_b200 as ua
+    from uniadapter_b200 import _lib
+    from oracle import synth
+    K, D = 21, 256           # 21 classes: uneven split for every cluster size
+    cfg = cases.CFG
+    dev = cuda_device
+    text = synth.unit_rows(K, D, 191)
+    x, _, _ = synth.features(3, 2, D, text, 192)
+    models = {}
+    for ks in (1, ksplit):
+        _lib.set_tuning("dota_ksplit", ks)
+        try:
+            m = ua.DOTA(cfg, D, K, torch.full((D, K), 0.001), device=dev)
+            for t in range(3):
+                h = A.head(x[t], text)
+                m.fit(cu(x[t], dev), cu(h["prob"], dev))
+        finally:
+            _lib.set_tuning("dota_ksplit", 0)
+        models[ks] = m
+    a, b = models[1], models[ksplit]
+    assert torch.equal(a.Sigma, b.Sigma) and torch.equal(a.mu, b.mu) and torch.equal(a.c, b.c)
+    np.testing.assert_allclose(b.overall_Sigma.cpu().numpy(), a.overall_Sigma.cpu().numpy(), rtol=1e-5, atol=1e-9)   # entries near zero cancel over the classes: absolute floor at 2e-6 of the diagonal scale, as in the golden test
