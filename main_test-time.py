@@ -70,7 +70,7 @@ def parse_args(argv=None):
     if not args.use_mode_dota:
         args.res_learning = False
     if args.lockstep is None:
-        args.lockstep = bool(args.use_mode_dota) and args.batch_size == 1 and args.vlm3d != 'openshape'
+        args.lockstep = bool(args.use_mode_dota or args.use_dota) and args.batch_size == 1 and args.vlm3d != 'openshape'
     return args
 
 
@@ -117,13 +117,16 @@ def main(argv=None):
         datasets = [NpyCorruptionStream(args.myroot, corruptions[s], args.severity, npoints=args.npoints) if args.myroot else
                     SyntheticStream(args.stream_length, args.npoints, args.num_classes, seed=args.seed, stream=s)
                     for s in mine]
-        results = test_zeroshot_3d_lockstep(datasets, model, args, names=[corruptions[s] for s in mine])
+        if args.use_mode_dota:      # all streams of this rank in one engine
+            results = test_zeroshot_3d_lockstep(datasets, model, args, names=[corruptions[s] for s in mine])
+        else:                       # DOTA branch: one graph-captured engine per stream, one after the other
+            results = [test_zeroshot_3d_lockstep([d], model, args, names=[corruptions[s]])[0] for d, s in zip(datasets, mine)]
         for s, result in zip(mine, results):
             local_results[s] = result
             if world > 1 or rank == 0:
                 print(f"[rank {rank}] {corruptions[s]}: acc1 {result['acc1']:.2f} acc3 {result['acc3']:.2f} acc5 "
                       f"{result['acc5']:.2f} ({result['ms_per_sample']:.3f} ms/sample incl. warm-up and graph capture, median "
-                      f"{result['median_ms_per_sample']:.3f}; {len(mine)} streams in lock-step)",
+                      f"{result['median_ms_per_sample']:.3f}; {len(mine) if args.use_mode_dota else 1} stream(s) per CUDA-graph step)",
                       flush=True)
         mine = []
     for s in mine:

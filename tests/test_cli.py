@@ -28,7 +28,7 @@ def test_flags_follow_the_reference_and_fix_d1():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("flags", [['--mode-M', '8'], ['--use-dota'], ['--mode-M', '4', '--no-res-learning'],
-                                   ['--mode-M', '8', '--no-lockstep']])
+                                   ['--mode-M', '8', '--no-lockstep'], ['--use-dota', '--no-lockstep']])
 def test_cli_runs_a_stream_on_the_gpu(flags, cuda_device, tmp_path):
     m = load_main()
     out = m.main(['--vlm3d', 'ulip', '--small-encoder', '--corruption', 'gaussian', '--stream-length', '5',
@@ -58,7 +58,7 @@ def test_cli_all_corruptions_in_lockstep(cuda_device, tmp_path):
     uniadapter_b200.adapter.test_zeroshot_3d_lockstep); every stream reports its own accuracies and predictions."""
     m = load_main()
     a = m.parse_args(['--vlm3d', 'ulip'])
-    assert a.lockstep and not m.parse_args(['--use-dota']).lockstep and not m.parse_args(['--batch-size', '4']).lockstep
+    assert a.lockstep and m.parse_args(['--use-dota']).lockstep and not m.parse_args(['--batch-size', '4']).lockstep
     out = m.main(['--vlm3d', 'ulip', '--small-encoder', '--corruption', 'all', '--stream-length', '6', '--num-classes',
                   '12', '--mode-M', '8', '--output-dir', str(tmp_path)])
     assert len(out) == 15

@@ -110,3 +110,31 @@ def test_stream_engine_cuda_graph(cuda_device):
     assert eng.graph is not None
     np.testing.assert_allclose(eng.adapter.c.sum(dim=(1, 2)).cpu().numpy(), inp["K"] + 2 * T, rtol=1e-5)
     assert float(eng.residuals.detach().abs().max()) > 0
+
+
+def test_dota_engine_cuda_graph(cuda_device):
+    """DOTA branch (full covariance) as one CUDA-graph replay per sample, cooperative SPD inverse included: invariants of
+    every step (finite logits, prediction = argmax, soft counts = K + samples, Lambda refreshed in place)."""
+    from uniadapter_b200.engine import DotaEngine
+    from uniadapter_b200.streams import unit_sphere_clouds
+    inp = cases.e2e_inputs("e2e_ulip_d2_modedota_res")
+    dev = cuda_device
+    T = 6
+    eng = DotaEngine(build(inp, dev, tensor_cores=True), 'ulip', torch.from_numpy(inp["text"]), inp["N"], cases.CFG, device=dev)
+    g = torch.Generator().manual_seed(5)
+    lam_ptr = eng.adapter.Lambda.data_ptr()
+    prev = None
+    for i in range(T):
+        final, pred = eng.step(unit_sphere_clouds(1, inp["N"], g).pin_memory())
+        assert torch.isfinite(final).all()
+        assert int(final.argmax(1)) == int(pred[0])
+        lam = eng.adapter.Lambda.float().clone()
+        assert torch.isfinite(lam).all() and (prev is None or not torch.equal(lam, prev))
+        prev = lam
+    assert eng.graph is not None and eng.adapter.Lambda.data_ptr() == lam_ptr
+    np.testing.assert_allclose(float(eng.adapter.c.sum()), inp["K"] + T, rtol=1e-6)
+    # A * Lambda = I for the matrix the last update inverted (fp16 Lambda: 1e-3 relative)
+    a = eng.adapter
+    reg = (1 - a.epsilon) * a.overall_Sigma.double() + a.epsilon * torch.eye(a.input_shape, device=dev, dtype=torch.float64)
+    resid = (reg @ a.Lambda.double() - torch.eye(a.input_shape, device=dev, dtype=torch.float64)).abs().max()
+    assert float(resid) < 5e-2

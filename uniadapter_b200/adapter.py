@@ -152,19 +152,24 @@ def test_zeroshot_3d_lockstep(datasets, model, args, names=None):
     the stacked state [S,K,M,D], one residual-learning call for S streams, the whole step replayed as a CUDA graph.
     With one dataset this is the per-sample loop of ``test_zeroshot_3d_core`` as a captured graph.
 
-    MODE-DOTA only (``--use-mode-dota``, with or without ``--res-learning``), batch size 1, rgb = ones (what every
-    dataset class of the reference returns). Returns one result dict per stream (acc1/acc3/acc5 in percent, preds) plus
+    MODE-DOTA (``--use-mode-dota``, with or without ``--res-learning``) for any number of streams; the DOTA branch
+    (``--use-dota``) for one stream per call (``engine.DotaEngine``). Batch size 1, rgb = ones (what every dataset class
+    of the reference returns). Returns one result dict per stream (acc1/acc3/acc5 in percent, preds) plus
     the per-step device times (reference event placement: host->device copy to fused logits)."""
-    from .engine import StreamEngine
+    from .engine import DotaEngine, StreamEngine
     from .streams import PinnedPrefetcher
     device = torch.device(args.device)
-    if not args.use_mode_dota:
-        raise NotImplementedError("lock-step streams run the MODE-DOTA path; use test_zeroshot_3d_core for --use-dota")
     cfg = {'epsilon': args.dota_epsilon, 'sigma': args.dota_sigma, 'eta': args.dota_eta, 'rho': args.dota_rho}
     text = load_text_features(args, device)
     S = len(datasets)
-    engine = StreamEngine(model, args.vlm3d, text, S, args.npoints, cfg, mode_M=args.mode_M,
-                          res_learning=bool(args.res_learning), device=device, use_graph=True, seed=args.seed)
+    if not args.use_mode_dota:
+        # the DOTA branch (full covariance): one stream per engine, the per-sample step as one CUDA-graph replay
+        if S != 1:
+            raise NotImplementedError("the DOTA branch runs one stream per engine (its covariance stack is per adapter)")
+        engine = DotaEngine(model, args.vlm3d, text, args.npoints, cfg, device=device, use_graph=True, seed=args.seed)
+    else:
+        engine = StreamEngine(model, args.vlm3d, text, S, args.npoints, cfg, mode_M=args.mode_M,
+                              res_learning=bool(args.res_learning), device=device, use_graph=True, seed=args.seed)
     feed = PinnedPrefetcher(datasets, args.npoints)
     hits = torch.zeros(S, 3)
     preds, times = [], []

@@ -62,7 +62,8 @@ class DOTA(nn.Module):
     @torch.no_grad()
     def update(self):
         if self._inv_ws is not None:
-            out = torch.empty((self.input_shape, self.input_shape), dtype=torch.float16, device=self.device)
+            # in place: Lambda keeps its storage from step to step (a captured CUDA graph reads and writes fixed addresses)
+            out = self.Lambda if self.Lambda.is_contiguous() else torch.empty_like(self.Lambda)
             rc = _lib.lib().ua_dota_update_f32(_lib.ptr(self.overall_Sigma), self.input_shape, float(self.epsilon),
                                                _lib.ptr(self._inv_ws), _lib.ptr(out), None, _lib.stream_ptr())
             _lib.check(rc, "ua_dota_update_f32")

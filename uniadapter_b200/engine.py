@@ -199,3 +199,62 @@ class StreamEngine:
         n = _lib.launch_count()
         self.use_graph = was_graph
         return n
+
+
+class DotaEngine:
+    """The DOTA branch (full covariance, ``--use-dota``, BASELINE cfg 1) of the per-sample loop as one CUDA-graph replay
+    per sample: tokenizer + encoder, head, predict on the current Lambda, fit, update (the cooperative SPD inverse) and
+    fusion, with static buffers. Same arithmetic as ``adapter.test_zeroshot_3d_core`` with ``use_dota``; the FPS start
+    index comes from the device generator (graph-safe). One stream: the (K,D,D) covariance stack of DOTA is 42 MB per
+    stream at cfg 1 and its kernels take one adapter per launch."""
+
+    def __init__(self, encoder, vlm3d, text, npoints, cfg, device='cuda', use_graph=True, seed=42):
+        from .dota import DOTA
+        self.dev = torch.device(device)
+        self.encoder, self.vlm3d, self.cfg = encoder, vlm3d, cfg
+        self.text = text.to(self.dev).float().contiguous()
+        self.K, self.D = self.text.shape
+        self.adapter = DOTA(cfg, self.D, self.K, torch.full((self.D, self.K), 0.001), device=self.dev)   # Uni_Adapter.py:329-330
+        self.pc = torch.zeros(1, npoints, 3, device=self.dev)
+        self.rgb = torch.ones(1, npoints, 3, device=self.dev)
+        self.final = torch.zeros(1, self.K, device=self.dev)
+        self.pred = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self._host_out = torch.empty(1, self.K, dtype=torch.float32).pin_memory()
+        self.use_graph, self.graph, self.step_idx = use_graph, None, 0
+        torch.cuda.manual_seed(seed)
+        from .encoders import set_device_rng
+        set_device_rng(encoder, True)
+
+    def _encode(self, pc):
+        if self.vlm3d == 'uni3d':
+            return self.encoder.encode_pc(torch.cat((pc, self.rgb), dim=-1))
+        if self.vlm3d == 'ulip':
+            return self.encoder(pc)
+        return self.encoder(pc, torch.cat((pc, self.rgb), dim=-1))
+
+    @torch.no_grad()
+    def _body(self):
+        a, cfg = self.adapter, self.cfg
+        feats, clip_logits, _, prob, _ = zero_shot_head(self._encode(self.pc), self.text)
+        dl = a.predict(feats.mean(0).unsqueeze(0).half())
+        a.fit(feats, prob)
+        a.update()
+        final, arg, _ = fuse_logits(clip_logits, dl, a.c, cfg['rho'], cfg['eta'], feats.shape[0], 'dota')
+        self.final.copy_(final)
+        self.pred.copy_(arg)
+
+    def step(self, pc_host: torch.Tensor):
+        """pc_host (1,N,3) pinned host tensor -> (final_logits (1,K) pinned host, pred (1,) device)."""
+        self.pc.copy_(pc_host, non_blocking=True)
+        if self.use_graph and self.step_idx >= 2:
+            if self.graph is None:
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph):
+                    self._body()
+            self.graph.replay()
+        else:
+            self._body()
+        self.step_idx += 1
+        self._host_out.copy_(self.final, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self._host_out, self.pred
