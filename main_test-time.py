@@ -70,7 +70,8 @@ def parse_args(argv=None):
     if not args.use_mode_dota:
         args.res_learning = False
     if args.lockstep is None:
-        args.lockstep = bool(args.use_mode_dota or args.use_dota) and args.batch_size == 1 and args.vlm3d != 'openshape'
+        args.lockstep = bool(args.use_mode_dota or args.use_dota) and args.batch_size == 1 and \
+            not (args.vlm3d == 'openshape' and not args.use_mode_dota)
     return args
 
 
@@ -115,7 +116,8 @@ def main(argv=None):
     if args.lockstep and mine:
         from uniadapter_b200.adapter import test_zeroshot_3d_lockstep
         datasets = [NpyCorruptionStream(args.myroot, corruptions[s], args.severity, npoints=args.npoints) if args.myroot else
-                    SyntheticStream(args.stream_length, args.npoints, args.num_classes, seed=args.seed, stream=s)
+                    SyntheticStream(args.stream_length, args.npoints, args.num_classes, seed=args.seed, stream=s,
+                                    colored=(args.vlm3d == 'openshape'))
                     for s in mine]
         if args.use_mode_dota:      # all streams of this rank in one engine
             results = test_zeroshot_3d_lockstep(datasets, model, args, names=[corruptions[s] for s in mine])

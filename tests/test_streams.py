@@ -38,3 +38,14 @@ def test_pinned_prefetcher_delivers_every_step_in_order():
     batch, labels = next(iter(first))
     for s in range(3):
         assert torch.equal(batch[s], streams[s][0][0])
+
+
+def test_pinned_prefetcher_with_rgb():
+    streams = [SyntheticStream(5, 48, 7, seed=2, stream=s, colored=True) for s in range(2)]
+    n = 0
+    for i, (xyz, labels, rgb) in enumerate(PinnedPrefetcher(streams, 48, with_rgb=True)):
+        for s in range(2):
+            assert torch.equal(xyz[s], streams[s][i][0]) and torch.equal(rgb[s], streams[s][i][3])
+            assert int(labels[s]) == streams[s][i][1]
+        n += 1
+    assert n == 5

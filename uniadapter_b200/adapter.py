@@ -170,15 +170,18 @@ def test_zeroshot_3d_lockstep(datasets, model, args, names=None):
     else:
         engine = StreamEngine(model, args.vlm3d, text, S, args.npoints, cfg, mode_M=args.mode_M,
                               res_learning=bool(args.res_learning), device=device, use_graph=True, seed=args.seed)
-    feed = PinnedPrefetcher(datasets, args.npoints)
+    colored = args.vlm3d == 'openshape' and args.use_mode_dota      # coloured streams: rgb travels with the cloud
+    feed = PinnedPrefetcher(datasets, args.npoints, with_rgb=colored)
     hits = torch.zeros(S, 3)
     preds, times = [], []
     start_event, end_event = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n = 0
-    for pc_host, labels in feed:
+    for item in feed:
+        pc_host, labels = item[0], item[1]
         torch.cuda.synchronize()
         start_event.record()
-        final, _ = engine.step(pc_host)                      # (S,K) pinned host logits; synchronised on return
+        # (S,K) pinned host logits; synchronised on return
+        final, _ = engine.step(pc_host, item[2]) if colored else engine.step(pc_host)
         end_event.record()
         torch.cuda.synchronize()
         times.append(start_event.elapsed_time(end_event))

@@ -77,18 +77,24 @@ class NpyCorruptionStream(Dataset):
 
 
 class PinnedPrefetcher:
-    """Feeds ``StreamEngine.step`` from S datasets: a background thread assembles the next (S,N,3) batch into one of two
+    """Feeds ``StreamEngine.step`` from S datasets: a background thread assembles the next (S,N,3) batch into one of a few
     pinned host buffers while the GPU works on the current one, so the host->device copy of a step always starts from
     pinned memory that is already filled (the engine's copy is asynchronous on its stream)."""
 
-    def __init__(self, datasets, npoints: int, depth: int = 2):
+    def __init__(self, datasets, npoints: int, depth: int = 2, with_rgb: bool = False):
+        """``with_rgb``: every item is (xyz, labels, rgb) instead of (xyz, labels), rgb in its own pinned (S,N,3) buffer:
+        for coloured streams (OpenShape); every dataset class of the reference returns rgb = ones."""
         import queue
         import threading
         self.datasets, self.N = datasets, npoints
         self.S = len(datasets)
+        self.with_rgb = with_rgb
         self.length = min(len(d) for d in datasets)
-        self.buffers = [torch.empty(self.S, npoints, 3).pin_memory() if torch.cuda.is_available()
-                        else torch.empty(self.S, npoints, 3) for _ in range(depth + 1)]
+
+        def pinned():
+            t = torch.empty(self.S, npoints, 3)
+            return t.pin_memory() if torch.cuda.is_available() else t
+        self.buffers = [(pinned(), pinned() if with_rgb else None) for _ in range(depth + 1)]
         self.free = queue.Queue()
         for b in self.buffers:
             self.free.put(b)
@@ -101,8 +107,10 @@ class PinnedPrefetcher:
             buf = self.free.get()
             labels = []
             for s, d in enumerate(self.datasets):
-                pc, label, _, _ = d[i]
-                buf[s].copy_(pc[: self.N])
+                pc, label, _, rgb = d[i]
+                buf[0][s].copy_(pc[: self.N])
+                if self.with_rgb:
+                    buf[1][s].copy_(rgb[: self.N])
                 labels.append(label)
             self.ready.put((buf, torch.tensor(labels)))
         self.ready.put(None)
@@ -114,6 +122,10 @@ class PinnedPrefetcher:
             if prev is not None:
                 self.free.put(prev)          # the engine has consumed it (step() synchronises on its result)
             if item is None:
+                self.thread.join()           # a daemon thread still alive at interpreter shutdown aborts the process
                 return
             prev = item[0]
-            yield item
+            if self.with_rgb:
+                yield item[0][0], item[1], item[0][1]
+            else:
+                yield item[0][0], item[1]
