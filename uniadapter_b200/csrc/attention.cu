@@ -399,23 +399,13 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
       }
       const float m_new = fmaxf(m_run, bmax);
       const float alpha = a_exp2(m_run - m_new);       // 0 at the first block (m_run = -inf)
-      // the previous PV must have finished before O is rescaled and before P is overwritten
-      if (j > 0) {
-        mbar_wait(o_done, ph ^ 1u);
-        a_fence_after();
-#pragma unroll 1
-        for (int c0 = 0; c0 < kHd; c0 += 32) {
-          float o[32];
-          a_tmem_ld32(t_o + lane_off + (uint32_t)c0, o);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] *= alpha;
-          a_tmem_st32(t_o + lane_off + (uint32_t)c0, o);
-        }
-      }
-      // pass 2: P = 2^(S - m_new) as a (hi, lo) pair into tensor memory, running sum
+      // pass 2: P = 2^(S - m_new) as a (hi, lo) pair into tensor memory, running sum. P_hi goes in place over S_j (a
+      // buffer PV_{j-1} does not touch); P_lo and the O accumulator are still being read / written by PV_{j-1}, so the
+      // first 64 columns are exponentiated and their P_hi stored BEFORE the wait for PV_{j-1}, their P_lo kept in
+      // registers until it is over (that wait was 9 % of the kernel's stall samples).
       float psum = 0.f;
-      auto weights = [&](uint32_t (&r)[32], int c0) {  // one 32-column chunk: P = 2^(S - m), split, store in place / P_lo
-        float hi[32], lo[32];
+      auto weights = [&](uint32_t (&r)[32], int c0, float (&lo)[32]) {   // one 32-column chunk; P_hi stored, P_lo returned
+        float hi[32];
         const int nv = kv_valid - c0;
         // (hi, lo) split of a weight by TRUNCATION (one LOP3 instead of a cvt.rna on the conversion pipe, which the
         // MUFU.EX2 of the same weight already loads): hi keeps 10 mantissa bits, lo = e - hi is exact (13 bits); the
@@ -438,20 +428,49 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
           }
         }
         a_tmem_st32(t_sj + lane_off + (uint32_t)c0, hi);     // in place: this thread's row, columns it has just read
-        a_tmem_st32(t_plo + lane_off + (uint32_t)c0, lo);
       };
+      float lo0[32], lo1[32];
+      const bool has1 = 32 < kv_valid;
+      {
+        uint32_t ra[32], rb[32];
+        a_tmem_ld32_issue(t_sj + lane_off, ra);
+        if (has1) a_tmem_ld32_issue(t_sj + lane_off + 32u, rb);
+        a_tmem_ld_wait(ra);
+        weights(ra, 0, lo0);
+        if (has1) {
+          a_tmem_ld_wait(rb);
+          weights(rb, 32, lo1);
+        }
+      }
+      // the previous PV must have finished before O is rescaled and before P_lo is overwritten
+      if (j > 0) {
+        mbar_wait(o_done, ph ^ 1u);
+        a_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < kKv; c0 += 64) {
+        for (int c0 = 0; c0 < kHd; c0 += 32) {
+          float o[32];
+          a_tmem_ld32(t_o + lane_off + (uint32_t)c0, o);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] *= alpha;
+          a_tmem_st32(t_o + lane_off + (uint32_t)c0, o);
+        }
+      }
+      a_tmem_st32(t_plo + lane_off, lo0);
+      if (has1) a_tmem_st32(t_plo + lane_off + 32u, lo1);
+#pragma unroll 1
+      for (int c0 = 64; c0 < kKv; c0 += 64) {
         if (c0 >= kv_valid) break;                     // the PV MMAs stop at ceil(kv_valid / 8) * 8 columns
         uint32_t ra[32], rb[32];
         const bool two = c0 + 32 < kv_valid;
         a_tmem_ld32_issue(t_sj + lane_off + (uint32_t)c0, ra);
         if (two) a_tmem_ld32_issue(t_sj + lane_off + (uint32_t)(c0 + 32), rb);
         a_tmem_ld_wait(ra);
-        weights(ra, c0);
+        weights(ra, c0, lo0);
+        a_tmem_st32(t_plo + lane_off + (uint32_t)c0, lo0);
         if (two) {
           a_tmem_ld_wait(rb);
-          weights(rb, c0 + 32);
+          weights(rb, c0 + 32, lo1);
+          a_tmem_st32(t_plo + lane_off + (uint32_t)(c0 + 32), lo1);
         }
       }
       a_tmem_st_wait();
