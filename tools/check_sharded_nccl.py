@@ -14,10 +14,9 @@ dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 cfg = {'epsilon': 1e-4, 'sigma': 1e-4, 'eta': 0.1, 'rho': 0.02}
 K, M, D, T = 1156, 8, 1024, 12
-# UA_SHARDED_GRAPH=1: steps >= 3 replay the CUDA graph of the step with the NCCL all-gather captured in it. Off by default:
-# the one attempt on 2 x B200 (torch 2.11, NCCL 2.28.9) did not return within 300 s and was not debugged further; the
-# graph replay itself is covered on one GPU (tests/test_gpu_adapters.py::test_class_sharded_step_as_cuda_graph).
-GRAPH_FROM = 3 if os.environ.get("UA_SHARDED_GRAPH") == "1" else T
+# steps >= GRAPH_FROM go through ShardedModeDota.step_graphed: two CUDA-graph replays around the eager NCCL all-gather
+# (UA_SHARDED_GRAPH=0 keeps every step eager)
+GRAPH_FROM = T if os.environ.get("UA_SHARDED_GRAPH") == "0" else 3
 text = torch.from_numpy(synth.unit_rows(K, D, 7)).to(dev)
 x, xa, _ = synth.features(T, 1, D, text.cpu().numpy(), 8)       # same on every rank (replicated encoder output)
 x, xa = torch.from_numpy(x * 2.5).float().to(dev), torch.from_numpy(xa * 1.5).float().to(dev)

@@ -224,27 +224,31 @@ class ShardedModeDota:
         return ShardedStepOutput(final, int(arg[0]), clip, dota)
 
     def step_graphed(self, feats_raw: torch.Tensor, feats_aug_raw: torch.Tensor) -> ShardedStepOutput:
-        """The same step as one CUDA-graph replay (the NCCL all-gather is captured with it): no host work between the
-        ~15 launches of a step, which is what bounds the eager step (0.3 ms for a 33 us cache pass). Call after at
-        least one eager ``step`` (communicator warm-up). Verified on one GPU (world 1 and emulated ranks); with a real
-        NCCL group the captured all-gather did not complete in the one 2-GPU attempt of round 1 (tools/check_sharded_nccl.py,
-        UA_SHARDED_GRAPH=1) -- the planned replacement is a peer-memory exchange kernel inside the same graph. ``pred`` of the result is a 1-element device tensor; inputs are
-        copied into static buffers, outputs are static buffers overwritten by the next replay."""
+        """The same step as two CUDA-graph replays around the one exchange: graph A = local head + cache logits into the
+        send buffer, then the all-gather (eager: NCCL stays outside the graphs), graph B = replicated softmax / fusion and
+        the local fits. No host work between the ~15 launches of a step, which is what bounds the eager step (0.3 ms for
+        a 33 us cache pass). Call after at least one eager ``step`` (communicator warm-up). ``pred`` of the result is a
+        1-element device tensor; inputs are copied into static buffers, outputs are static buffers overwritten by the
+        next replay. (Capturing the NCCL all-gather INSIDE one graph did not complete in the one 2-GPU attempt of round 1;
+        the planned replacement for the eager collective is a peer-memory exchange kernel.)"""
         if self._graph is None:
             self._g_in = feats_raw.clone().contiguous()
             self._g_aug = feats_aug_raw.clone().contiguous()
             # sum(c) so far in closed form (H7): K initial counts + one per fitted row
             self._g_counts = torch.full((1,), closed_form_count_sum(self.K, self.fits, feats_raw.shape[0]),
                                         dtype=torch.float32, device=feats_raw.device)
-            self._graph = torch.cuda.CUDAGraph()
             fits_before = self.fits
-            with torch.cuda.graph(self._graph):
+            ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ga):
                 self.local_logits(self._g_in)
-                self._all_gather()
+            with torch.cuda.graph(gb, pool=ga.pool()):       # graph B reads graph A's xnorm: one memory pool
                 self._g_out = self.finish(self._g_aug, device_counts=self._g_counts)
+            self._graph = (ga, gb)
             self.fits = fits_before       # capture runs no kernel: the counters advance on replay
         self._g_in.copy_(feats_raw)
         self._g_aug.copy_(feats_aug_raw)
-        self._graph.replay()
+        self._graph[0].replay()
+        self._all_gather()                                              # the one exchange of the step
+        self._graph[1].replay()
         self.fits += 2
         return self._g_out
