@@ -472,3 +472,25 @@ def test_dota_fit_class_split_over_a_cluster(ksplit, cuda_device):
     a, b = models[1], models[ksplit]
     assert torch.equal(a.Sigma, b.Sigma) and torch.equal(a.mu, b.mu) and torch.equal(a.c, b.c)
     np.testing.assert_allclose(b.overall_Sigma.cpu().numpy(), a.overall_Sigma.cpu().numpy(), rtol=1e-5, atol=1e-9)   # entries near zero cancel over the classes: absolute floor at 2e-6 of the diagonal scale, as in the golden test
+
+
+def test_mode_dota_batched_predict_only(cuda_device):
+    """predict() on 16 rows (batched cluster kernel, no fit) against 16 single-row predicts (single-sample kernel) on the
+    same adapted state; the state must not change."""
+    import uniadapter_b200 as ua
+    from oracle import synth
+    K, M, D = 23, 8, 512
+    cfg = cases.CFG
+    dev = cuda_device
+    text = synth.unit_rows(K, D, 301)
+    x, xa, _ = synth.features(2, 16, D, text, 302)
+    model = ua.DOTA_mix(cfg, D, K, cu(text, dev).t().contiguous(), num_modes=M, device=dev)
+    h = A.head(x[0], text)
+    model.fit(cu(x[0], dev), cu(h["prob"], dev))                 # a non-trivial state first
+    before = [t.clone() for t in (model.mu, model.var, model.pi, model.c)]
+    xq = cu(xa[1], dev)
+    batched = model.predict(xq)
+    single = torch.cat([model.predict(xq[i:i + 1]) for i in range(16)])
+    np.testing.assert_allclose(batched.cpu().numpy(), single.cpu().numpy(), rtol=1e-4, atol=logit_atol(D))
+    for a, b in zip(before, (model.mu, model.var, model.pi, model.c)):
+        assert torch.equal(a, b)
