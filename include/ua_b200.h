@@ -233,6 +233,18 @@ long long ua_dota_update_workspace_bytes(int D);
 int ua_dota_update_f32(const float* overall, int D, float eps, void* workspace, void* out_lambda_h,
                        float* out_lambda_f32, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Class-sharded cache: all-gather of the per-rank logits through NVLink peer memory, one CTA, inside the
+ * step's stream / CUDA graph. Replaces the torch.distributed.all_gather of the sharded step (the reference has no
+ * multi-GPU path; this is the exchange step of BASELINE cfg 4).
+ *   send [n] f32 of this rank; peer_recv_ptrs: DEVICE array [P] of float* (every rank's symmetric receive buffer,
+ *   2*P*n floats each, mapped into this process); peer_flag_ptrs: device array [P] of int* (every rank's P flags,
+ *   zero-initialised); seq: device int, the exchange counter (advanced by the kernel; all ranks start from 0);
+ *   local_out [P*n]: the gathered block in rank order; err: device int, set non-zero when a peer did not arrive in ~3 s.
+ * ---------------------------------------------------------------------------------------- */
+int ua_p2p_allgather_f32(const float* send, int n, const void* peer_recv_ptrs, const void* peer_flag_ptrs, int rank,
+                         int P, int* seq, float* local_out, int* err, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

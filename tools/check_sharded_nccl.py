@@ -21,6 +21,9 @@ text = torch.from_numpy(synth.unit_rows(K, D, 7)).to(dev)
 x, xa, _ = synth.features(T, 1, D, text.cpu().numpy(), 8)       # same on every rank (replicated encoder output)
 x, xa = torch.from_numpy(x * 2.5).float().to(dev), torch.from_numpy(xa * 1.5).float().to(dev)
 shard = PP.ShardedModeDota(cfg, text, M, lambda ts: PP.CudaShardOps(cfg, D, ts, M, dev))
+P2P = os.environ.get("UA_SHARDED_P2P") == "1"      # peer-memory exchange kernel instead of the NCCL all-gather
+if P2P:
+    shard.enable_p2p()
 full = ua.DOTA_mix(cfg, D, K, text.t().contiguous(), num_modes=M, device=dev)
 ok = True
 times = []
@@ -49,6 +52,8 @@ dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
     print(json.dumps({"check": "class_sharded_modedota_nccl", "world": world, "classes_per_rank": shard.k_hi - shard.k_lo,
                       "all_ranks_match_unsharded": bool(flag.item()), "sharded_step_ms_max_over_ranks": round(float(tmax[0]), 4),
-                      "graphed_step_ms_max_over_ranks": None if GRAPH_FROM >= T else round(float(tmax[1]), 4)}))
+                      "graphed_step_ms_max_over_ranks": None if GRAPH_FROM >= T else round(float(tmax[1]), 4),
+                      "exchange": "p2p kernel (symmetric memory, one graph)" if P2P else "nccl all_gather",
+                      "p2p_err": int(shard._p2p_err.item()) if P2P else None}))
 dist.destroy_process_group()
 sys.exit(0 if flag.item() else 1)

@@ -55,6 +55,7 @@ SIGNATURES = {
     "ua_dota_fit_f32": (_I, [_P, _P, _I, _P, _P, _P, _P, _I, _I, _P]),
     "ua_dota_predict_f16": (_I, [_P, _I, _P, _P, _I, _I, _P, _P]),
     "ua_dota_regularize_f32": (_I, [_P, _I, _F, _P, _P]),
+    "ua_p2p_allgather_f32": (_I, [_P, _I, _P, _P, _I, _I, _P, _P, _P, _P]),
     "ua_dota_update_workspace_bytes": (C.c_longlong, [_I]),
     "ua_dota_update_f32": (_I, [_P, _I, _F, _P, _P, _P, _P]),
 }

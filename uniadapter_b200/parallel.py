@@ -171,9 +171,42 @@ class ShardedModeDota:
         self.recv = self.ops.empty(self.world, 2, self.K_pad)
         self._graph = None
 
+    def enable_p2p(self):
+        """Replace the NCCL all-gather of the step by the peer-memory exchange kernel (csrc/p2p.cu): symmetric receive
+        and flag buffers from torch.distributed._symmetric_memory (mapped into every rank's address space), one CTA per
+        rank pushes its logits into every peer's buffer over NVLink and waits for the peers' flags. With it the whole
+        step (local logits -> exchange -> replicated softmax / fusion -> local fits) is ONE CUDA graph."""
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        dev = self.send.device
+        n, P = self.send.numel(), self.world
+        group = self.group if self.group is not None else dist.group.WORLD
+        self._sym_recv = symm_mem.empty(2 * P * n, dtype=torch.float32, device=dev)
+        self._sym_flag = symm_mem.empty(P, dtype=torch.int32, device=dev)
+        self._sym_recv.zero_()
+        self._sym_flag.zero_()
+        h_recv = symm_mem.rendezvous(self._sym_recv, group)
+        h_flag = symm_mem.rendezvous(self._sym_flag, group)
+        self._p2p_recv_ptrs = torch.tensor(list(h_recv.buffer_ptrs), dtype=torch.int64, device=dev)
+        self._p2p_flag_ptrs = torch.tensor(list(h_flag.buffer_ptrs), dtype=torch.int64, device=dev)
+        self._p2p_seq = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._p2p_err = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._p2p_handles = (h_recv, h_flag)
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)          # every rank has zeroed its flags before anybody signals
+        self._p2p = True
+
     def _all_gather(self):
         if self.gather_fn is not None:
             self.gather_fn(self)
+            return
+        if getattr(self, '_p2p', False):
+            from . import _lib
+            rc = _lib.lib().ua_p2p_allgather_f32(_lib.ptr(self.send), self.send.numel(), _lib.ptr(self._p2p_recv_ptrs),
+                                                 _lib.ptr(self._p2p_flag_ptrs), self.rank, self.world,
+                                                 _lib.ptr(self._p2p_seq), _lib.ptr(self.recv), _lib.ptr(self._p2p_err),
+                                                 _lib.stream_ptr())
+            _lib.check(rc, "ua_p2p_allgather_f32")
             return
         if self.world == 1:
             self.recv[0].copy_(self.send)
@@ -238,17 +271,26 @@ class ShardedModeDota:
             self._g_counts = torch.full((1,), closed_form_count_sum(self.K, self.fits, feats_raw.shape[0]),
                                         dtype=torch.float32, device=feats_raw.device)
             fits_before = self.fits
-            ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-            with torch.cuda.graph(ga):
-                self.local_logits(self._g_in)
-            with torch.cuda.graph(gb, pool=ga.pool()):       # graph B reads graph A's xnorm: one memory pool
-                self._g_out = self.finish(self._g_aug, device_counts=self._g_counts)
-            self._graph = (ga, gb)
+            ga = torch.cuda.CUDAGraph()
+            if getattr(self, '_p2p', False):                 # peer-memory exchange: the whole step is one graph
+                with torch.cuda.graph(ga):
+                    self.local_logits(self._g_in)
+                    self._all_gather()
+                    self._g_out = self.finish(self._g_aug, device_counts=self._g_counts)
+                self._graph = (ga, None)
+            else:
+                gb = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(ga):
+                    self.local_logits(self._g_in)
+                with torch.cuda.graph(gb, pool=ga.pool()):   # graph B reads graph A's xnorm: one memory pool
+                    self._g_out = self.finish(self._g_aug, device_counts=self._g_counts)
+                self._graph = (ga, gb)
             self.fits = fits_before       # capture runs no kernel: the counters advance on replay
         self._g_in.copy_(feats_raw)
         self._g_aug.copy_(feats_aug_raw)
         self._graph[0].replay()
-        self._all_gather()                                              # the one exchange of the step
-        self._graph[1].replay()
+        if self._graph[1] is not None:
+            self._all_gather()                                          # the one exchange of the step (NCCL, eager)
+            self._graph[1].replay()
         self.fits += 2
         return self._g_out
