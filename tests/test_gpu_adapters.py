@@ -494,3 +494,39 @@ def test_mode_dota_batched_predict_only(cuda_device):
     np.testing.assert_allclose(batched.cpu().numpy(), single.cpu().numpy(), rtol=1e-4, atol=logit_atol(D))
     for a, b in zip(before, (model.mu, model.var, model.pi, model.c)):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("P_", [1, 2, 4])
+def test_p2p_allgather_kernel_emulated_ranks(P_, cuda_device):
+    """csrc/p2p.cu on one GPU: P emulated ranks (own receive / flag buffers, one stream each, so that the P one-CTA
+    kernels of an exchange run concurrently) push into each other's buffers, signal and wait; 6 exchanges: every rank must
+    receive every rank's vector of that exchange (parity double buffer, device-side sequence numbers), no time-outs.
+    (The real thing - buffers of other GPUs mapped through torch symmetric memory - runs in tools/check_sharded_nccl.py.)"""
+    from uniadapter_b200 import _lib
+    dev = cuda_device
+    n = 37
+    recv = [torch.zeros(2 * P_ * n, device=dev) for _ in range(P_)]
+    flag = [torch.zeros(P_, dtype=torch.int32, device=dev) for _ in range(P_)]
+    recv_ptrs = torch.tensor([t.data_ptr() for t in recv], dtype=torch.int64, device=dev)
+    flag_ptrs = torch.tensor([t.data_ptr() for t in flag], dtype=torch.int64, device=dev)
+    seq = [torch.zeros(1, dtype=torch.int32, device=dev) for _ in range(P_)]
+    err = [torch.zeros(1, dtype=torch.int32, device=dev) for _ in range(P_)]
+    out = [torch.zeros(P_ * n, device=dev) for _ in range(P_)]
+    send = [torch.zeros(n, device=dev) for _ in range(P_)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(P_)]
+    torch.cuda.synchronize()
+    for step in range(6):
+        for r in range(P_):
+            send[r].copy_(torch.arange(n, device=dev, dtype=torch.float32) + 1000 * r + 100000 * step)
+        torch.cuda.synchronize()
+        for r in range(P_):
+            with torch.cuda.stream(streams[r]):
+                rc = _lib.lib().ua_p2p_allgather_f32(_lib.ptr(send[r]), n, _lib.ptr(recv_ptrs), _lib.ptr(flag_ptrs), r, P_,
+                                                     _lib.ptr(seq[r]), _lib.ptr(out[r]), _lib.ptr(err[r]),
+                                                     streams[r].cuda_stream)
+                _lib.check(rc, "ua_p2p_allgather_f32")
+        torch.cuda.synchronize()
+        expect = torch.cat(send)
+        for r in range(P_):
+            assert int(err[r]) == 0 and int(seq[r]) == step + 1
+            assert torch.equal(out[r], expect)
