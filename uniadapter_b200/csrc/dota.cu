@@ -1,5 +1,5 @@
 // DOTA (full-covariance) cache kernels for sm_100a. Replaces dota.py:41-63 (fit) and :72-87 (predict);
-// dota.py:66-69 (update) keeps its library inverse, fed by ua_dota_regularize_f32.
+// dota.py:66-69 (update) is csrc/spdinv.cu; ua_dota_regularize_f32 feeds the library inverse kept for widths that kernel does not take.
 //
 // fit is a pure HBM stream over Sigma [K,D,D] (read + write once, 8*K*D^2 bytes): each thread owns one float4 of a
 // (row, 4 columns) position and walks the K classes, applying the rank-B update and accumulating the class mean
