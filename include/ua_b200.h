@@ -52,12 +52,18 @@ int ua_set_tuning(const char* key, int value);
  * running min initialised to 1e10, argmax takes the FIRST maximal index.
  *   xyz        [B,N,3] f32
  *   start_idx  [B] i64, or NULL for start index 0 in every cloud
- *   skip_small_norm  != 0: points with x*x+y*y+z*z <= 1e-3 are never selected/updated (pointnet2_ops quirk)
+ *   skip_small_norm  bit 0: points with x*x+y*y+z*z <= 1e-3 are never selected/updated (pointnet2_ops quirk, in the
+ *              torch arithmetic above); UA_FPS_POINTNET2 (bit 1): the published pointnet2_ops kernel's own arithmetic
+ *              (erikwijmans/Pointnet2_PyTorch pointnet2_ops_lib 3.0.0, sampling_gpu.cu; the un-vendored extension behind
+ *              models/point_encoder.py:12): d = fma(dz,dz, fma(dx,dx, dy*dy)) (nvcc's contraction of the upstream
+ *              expression), points with fma(z,z, fma(x,x, y*y)) <= 1e-3 (double compare) never take part, ties follow
+ *              upstream's left-biased reduction tree (lowest bit-reversed owner thread k mod bs, then lowest k), bs = largest power of two <= min(N, 512); N <= UA_FPS_MAX_REG_POINTS.
  *   out_idx    [B,G] i32 or i64 (idx_is_i64), may be NULL
  *   out_centers[B,G,3] f32, may be NULL
  *   scratch    [B,N] f32, only required when N > UA_FPS_MAX_REG_POINTS (else may be NULL)
  */
 #define UA_FPS_MAX_REG_POINTS 16384
+#define UA_FPS_POINTNET2 2
 int ua_fps_f32(const float* xyz, int B, int N, int G, const int64_t* start_idx, int skip_small_norm,
                void* out_idx, int idx_is_i64, float* out_centers, float* scratch, void* stream);
 
@@ -133,6 +139,16 @@ int ua_modedota_step_f32(const float* x_pred, int Bp, const float* x_fit, const 
                          int ldg, int k_gamma_offset, float* mu, float* var, float* pi, float* c,
                          float* class_counts, int S, int K, int M, int D, float eps, float* out_logits, int ldo,
                          int k_out_offset, void* stream);
+
+/* Per-stream random inputs of a lock-step step, drawn on the device (CUDA-graph safe): the N(0,1) jitter of the
+ * augmented view (Uni_Adapter.py:420-421) and the random FPS start indices of both views (models/ulip/pointbert/
+ * misc.py:52, models/openshape/pointnet_util.py:77). Counter-based Philox4x32-10 keyed by seeds[s], counter = (element,
+ * *step, purpose): a stream's draws depend only on its own seed and its own step count, not on the co-resident
+ * streams or the world size. The kernel advances *step (device memory) itself; done_counter is a zeroed u32 scratch.
+ *   noise [S, per_stream] f32; start_idx [2,S] i64 in [0, n_range) (first view, jittered view) or NULL
+ */
+int ua_stream_rng_f32(const int64_t* seeds, int64_t* step, int S, int64_t per_stream, float* noise,
+                      int64_t* start_idx, int n_range, uint32_t* done_counter, void* stream);
 
 /* Fusion of zero-shot and cache logits, Uni_Adapter.py:491-521 (MODE-DOTA, mode=1) or
  * dota_mixture.py:289-293 (DOTA, mode=0: final = clip + w*dota).

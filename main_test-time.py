@@ -120,9 +120,13 @@ def main(argv=None):
                                     colored=(args.vlm3d == 'openshape'))
                     for s in mine]
         if args.use_mode_dota:      # all streams of this rank in one engine
+            args.stream_ids = list(mine)        # per-stream generators keyed by the GLOBAL stream index
             results = test_zeroshot_3d_lockstep(datasets, model, args, names=[corruptions[s] for s in mine])
         else:                       # DOTA branch: one graph-captured engine per stream, one after the other
-            results = [test_zeroshot_3d_lockstep([d], model, args, names=[corruptions[s]])[0] for d, s in zip(datasets, mine)]
+            results = []
+            for d, s in zip(datasets, mine):
+                args.stream_ids = [s]
+                results.append(test_zeroshot_3d_lockstep([d], model, args, names=[corruptions[s]])[0])
         for s, result in zip(mine, results):
             local_results[s] = result
             if world > 1 or rank == 0:

@@ -65,6 +65,15 @@ E2E = {
     "e2e_ulip_d2_modedota": (8, 1024, 40, 8, 2, False, 72),
     "e2e_ulip_d2_dota": (6, 1024, 40, 0, 2, False, 73),
 }
+# OpenShape (cfg 3): name -> (T steps, N points, S patches, K classes, M modes, depth, seed); D = 1280, rgb ~ U[0,1)
+E2E_OSHAPE = {
+    "e2e_oshape_d2_modedota": (5, 10000, 384, 15, 8, 2, 81),
+}
+# Uni3D front end (cfg 4/5 geometry): name -> (B, N, G, k, encoder dim, trans dim, seed)
+UNI3D_FRONT = {
+    "uni3d_front_b1_n10000": (1, 10000, 512, 64, 512, 1024, 91),
+    "uni3d_front_b2_n1024": (2, 1024, 512, 64, 512, 1024, 92),
+}
 E2E_MODEL_SEED = 0
 E2E_LOOP_SEED = 123
 
@@ -73,6 +82,17 @@ def e2e_inputs(name):
     T, N, K, M, depth, res, seed = E2E[name]
     return dict(pc=synth.cloud(T, N, seed), text=synth.unit_rows(K, 512, seed + 1), T=T, N=N, K=K, M=M, depth=depth,
                 res_learning=res)
+
+
+def e2e_oshape_inputs(name):
+    T, N, S, K, M, depth, seed = E2E_OSHAPE[name]
+    return dict(pc=synth.cloud(T, N, seed), rgb=synth.uniform((T, N, 3), seed + 2), text=synth.unit_rows(K, 1280, seed + 1),
+                T=T, N=N, S=S, K=K, M=M, depth=depth)
+
+
+def uni3d_front_inputs(name):
+    B, N, G, k, enc, trans, seed = UNI3D_FRONT[name]
+    return dict(xyz=synth.cloud(B, N, seed), rgb=synth.uniform((B, N, 3), seed + 1), B=B, N=N, G=G, k=k, enc=enc, trans=trans)
 
 
 def tok_knn_inputs(name):

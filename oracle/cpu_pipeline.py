@@ -20,9 +20,10 @@ from . import tokenizer as T
 class OracleGroup(torch.nn.Module):
     """CPU stand-in for the group divider (FPS + kNN + centre subtraction) backed by the C oracle."""
 
-    def __init__(self, num_group, group_size, random_start, threads=1):
+    def __init__(self, num_group, group_size, random_start, threads=1, pointnet2=False):
         super().__init__()
         self.num_group, self.group_size, self.random_start, self.threads = num_group, group_size, random_start, threads
+        self.pointnet2 = pointnet2          # Uni3D: the published pointnet2_ops FPS (oracle_fps_pointnet2)
         self.next_start_idx = None
 
     def forward(self, xyz, color=None):
@@ -33,7 +34,8 @@ class OracleGroup(torch.nn.Module):
         elif self.random_start:
             start = torch.randint(0, N, (B,), dtype=torch.long).numpy()     # misc.py:52
         g = T.group_knn(xyz.numpy(), self.num_group, self.group_size, rgb=None if color is None else color.numpy(),
-                        start_idx=start, threads=self.threads, sort_by_index=True)
+                        start_idx=start, threads=self.threads, sort_by_index=True,
+                        pointnet2=self.pointnet2 and start is None)
         if color is None:
             return torch.from_numpy(g["neigh"]), torch.from_numpy(g["center"])
         return torch.from_numpy(g["neigh"]), torch.from_numpy(g["center"]), torch.from_numpy(g["feat"])
@@ -59,7 +61,8 @@ def cpu_encoder_like(gpu_or_fresh_encoder, threads=1):
             parts = name.split(".")
             for p in parts[:-1]:
                 parent = getattr(parent, p)
-            setattr(parent, parts[-1], OracleGroup(mod.num_group, mod.group_size, mod.random_start, threads))
+            setattr(parent, parts[-1], OracleGroup(mod.num_group, mod.group_size, mod.random_start, threads,
+                                                       getattr(mod, 'pointnet2', False)))
         if mod.__class__.__name__ == "_SetAbstraction":
             sa = mod
 

@@ -220,7 +220,7 @@ def e2e_goldens():
             res = torch.zeros_like(text, requires_grad=True)
             opt = torch.optim.Adam([res], lr=0.001)
         torch.manual_seed(cases.E2E_LOOP_SEED)
-        finals, clips, dls = [], [], []
+        finals, clips, dls, lambdas, overall_diag = [], [], [], [], []
         with torch.no_grad():
             for i in range(T):
                 pc = pcs[i:i + 1]
@@ -260,12 +260,111 @@ def e2e_goldens():
                     final = wc * clip_logits + wd * d
                 else:
                     adapter.update()
+                    lambdas.append(adapter.Lambda.clone())                     # fp16 (D,D) after this step's update
+                    overall_diag.append(torch.diagonal(adapter.overall_Sigma).clone())
                     w = torch.clamp(CFG['rho'] * adapter.c.mean() / feats.size(0), max=CFG['eta'])
                     final = (clip_logits + w * dl).float()
                 finals.append(final), clips.append(clip_logits), dls.append(dl.float())
         extra = dict(residual=res.detach()) if inp["res_learning"] else {}
+        if not use_mode:
+            extra.update(Lambda=torch.stack(lambdas), overall_diag=torch.stack(overall_diag), mu=adapter.mu, c=adapter.c)
         save(name, inp, final_logits=torch.cat(finals), clip_logits=torch.cat(clips), dota_logits=torch.cat(dls),
              pred=torch.cat(finals).argmax(1).to(torch.int32), **extra)
+
+
+def e2e_openshape_goldens():
+    """cfg 3: the reference's per-sample MODE-DOTA loop (Uni_Adapter.py:368-521, batch 1) around its own OpenShape
+    PointPatchTransformer (models/openshape/ppta.py:85-148,181-186 = scaling 4, at reduced depth) with FPS + ball query
+    + sample_and_group from models/openshape/pointnet_util.py, coloured clouds of 10 000 points, on the CPU."""
+    from uniadapter_b200.encoders import OpenShapePPAT
+    _, ppta = R.openshape_ppta()
+    ua = R.uni_adapter()
+    dm = R.dota_mixture()
+    for name in cases.E2E_OSHAPE:
+        inp = cases.e2e_oshape_inputs(name)
+        T, N, S, K, M, depth = inp["T"], inp["N"], inp["S"], inp["K"], inp["M"], inp["depth"]
+        torch.manual_seed(cases.E2E_MODEL_SEED)
+        ref = ppta.Projected('global', ppta.PointPatchTransformer('global', None, 512, depth, 8, 512 * 3, 256, S, 0.2, 64, 6),
+                             torch.nn.Linear(512, 1280)).eval()                    # ppta.py:181-186 at `depth`
+        torch.manual_seed(cases.E2E_MODEL_SEED)
+        mine = OpenShapePPAT(depth=depth, patches=S).eval()
+        ref_sd = [v for k, v in ref.state_dict().items()]
+        my_sd = [v for k, v in mine.state_dict().items()]
+        assert len(ref_sd) == len(my_sd) and all(a.shape == b.shape and torch.equal(a, b) for a, b in zip(ref_sd, my_sd)), \
+            "OpenShapePPAT does not reproduce the reference's random init"
+        text, pcs, rgbs = T_(inp["text"]), T_(inp["pc"]), T_(inp["rgb"])
+        args = types.SimpleNamespace(vlm3d='openshape')
+        adapter = dm.DOTA_mix(CFG, 1280, K, text.t().contiguous(), num_modes=M)
+        torch.manual_seed(cases.E2E_LOOP_SEED)
+        finals, clips, dls = [], [], []
+        with torch.no_grad():
+            for i in range(T):
+                pc, rgb = pcs[i:i + 1], rgbs[i:i + 1]
+                feature = torch.cat((pc, rgb), dim=-1)
+                clip_weights = text.t()
+                feats, clip_logits, loss, prob_map, pred = ua.get_logits_wrapper(args, ref, feature, clip_weights)
+                dl = adapter.predict(feats.mean(0).unsqueeze(0).half())
+                adapter.fit(feats, prob_map)
+                pc_aug = pc + 0.05 * torch.randn_like(pc)
+                feats_aug, _, _, _, _ = ua.get_logits_wrapper(args, ref, torch.cat((pc_aug, rgb), dim=-1), clip_weights)
+                feats_aug = feats_aug / feats_aug.norm(dim=-1, keepdim=True)
+                adapter.fit(feats_aug, prob_map)
+                adapter.update()
+                w = torch.clamp(CFG['rho'] * adapter.c.mean() / feats.size(0), max=CFG['eta'])
+                d = w * dl
+                ec, ed = ua.softmax_entropy(clip_logits), ua.softmax_entropy(d)
+                wc, wd = 1 / (ec + 1e-3), 1 / (ed + 1e-3)
+                wc = wc / (wc + wd)
+                wd = wd / (wc + wd)
+                final = wc * clip_logits + wd * d
+                finals.append(final), clips.append(clip_logits), dls.append(dl.float())
+        save(name, inp, final_logits=torch.cat(finals), clip_logits=torch.cat(clips), dota_logits=torch.cat(dls),
+             pred=torch.cat(finals).argmax(1).to(torch.int32), c=adapter.c, pi=adapter.pi,
+             mu_sample=adapter.mu[:, :, ::8].contiguous())
+
+
+def uni3d_front_goldens():
+    """Uni3D front end up to the transformer blocks: the reference's Group.forward + Encoder + encoder2trans + position
+    embedding (models/point_encoder.py:93-159,192-208) on 10 000-point coloured clouds. Its FPS is the un-vendored
+    pointnet2_ops extension: the stub below answers furthest_point_sample with the oracle's restatement of the PUBLISHED
+    kernel (oracle_fps_pointnet2) -- everything after the indices is the reference's own code. The timm EVA02 blocks are
+    absent and not a parity target: a recorder stands in for the first block and keeps its input."""
+    from oracle import tokenizer as OT
+    from uniadapter_b200.encoders import Uni3DEncoder
+    u3 = R.uni3d_point_encoder()
+
+    def furthest_point_sample(data, number):
+        return torch.from_numpy(OT.fps_pointnet2(data.numpy(), number, threads=4)).to(torch.int32)
+
+    def gather_operation(features, idx):
+        return torch.gather(features, 2, idx.long().unsqueeze(1).expand(-1, features.shape[1], -1))
+
+    u3.pointnet2_utils.furthest_point_sample = furthest_point_sample
+    u3.pointnet2_utils.gather_operation = gather_operation
+
+    class Recorder(torch.nn.Module):
+        def forward(self, x):
+            self.seen = x.clone()
+            return x
+
+    for name in cases.UNI3D_FRONT:
+        inp = cases.uni3d_front_inputs(name)
+        rec = Recorder()
+        visual = types.SimpleNamespace(pos_drop=torch.nn.Identity(), blocks=[rec], norm=torch.nn.Identity(),
+                                       fc_norm=torch.nn.Identity())
+        args = types.SimpleNamespace(pc_feat_dim=inp["trans"], embed_dim=1024, group_size=inp["k"], num_group=inp["G"],
+                                     pc_encoder_dim=inp["enc"], patch_dropout=0.0)
+        torch.manual_seed(cases.E2E_MODEL_SEED)
+        ref = u3.PointcloudEncoder(visual, args).eval()
+        torch.manual_seed(cases.E2E_MODEL_SEED)
+        mine = Uni3DEncoder(depth=0).eval()
+        for k_, v in ref.state_dict().items():
+            assert torch.equal(v, mine.state_dict()[k_]), f"Uni3DEncoder init differs from the reference at {k_}"
+        with torch.no_grad():
+            ref(T_(inp["xyz"]), T_(inp["rgb"]))
+            _, center, _ = ref.group_divider(T_(inp["xyz"]), T_(inp["rgb"]))
+        save(name, inp, center=center, x_pre_sample=rec.seen[:, :, ::8].contiguous(),
+             x_pre_rowsum=rec.seen.double().sum(-1).float())
 
 
 def main():
@@ -273,7 +372,8 @@ def main():
         sys.exit("reference not found at " + R.REF_ROOT)
     torch.set_num_threads(8)
     groups = dict(tokenizer=tokenizer_goldens, head=head_goldens, modedota=mode_dota_goldens, dota=dota_goldens,
-                  alignment=alignment_goldens, e2e=e2e_goldens)
+                  alignment=alignment_goldens, e2e=e2e_goldens,
+                  e2e_openshape=e2e_openshape_goldens, uni3d_front=uni3d_front_goldens)
     for name in (sys.argv[1:] or list(groups)):       # python -m oracle.make_golden [group ...]
         print(name), groups[name]()
 

@@ -94,6 +94,49 @@ def openshape_pointnet_util():
     return _load("models/openshape/pointnet_util.py", "ref_openshape_pointnet_util")
 
 
+def _install_redstone_stub():
+    """torch_redstone is absent; ppta.py uses two of its helpers: ``Lambda`` (a module around a function) and
+    ``supercat`` (concatenate after broadcasting the other dimensions)."""
+    import torch
+    import torch.nn as nn
+
+    class Lambda(nn.Module):
+        def __init__(self, fn):
+            super().__init__()
+            self.fn = fn
+
+        def forward(self, *a, **k):
+            return self.fn(*a, **k)
+
+    def supercat(tensors, dim=0):
+        nd = max(t.dim() for t in tensors)
+        ts = [t.reshape((1,) * (nd - t.dim()) + tuple(t.shape)) for t in tensors]
+        d = dim % nd
+        shape = [max(t.shape[i] for t in ts) for i in range(nd)]
+        out = []
+        for t in ts:
+            tgt = list(shape)
+            tgt[d] = t.shape[d]
+            out.append(t.expand(*tgt))
+        return torch.cat(out, dim=d)
+
+    _stub("torch_redstone", Lambda=Lambda, supercat=supercat)
+
+
+def openshape_ppta():
+    """models/openshape/{pointnet_util,ppta}.py under a fake package (the real __init__ pulls more dependencies)."""
+    install_stubs()
+    _install_redstone_stub()
+    pkg = "ref_openshape"
+    if pkg not in sys.modules:
+        p = types.ModuleType(pkg)
+        p.__path__ = [os.path.join(REF_ROOT, "models/openshape")]
+        sys.modules[pkg] = p
+    pu = _load("models/openshape/pointnet_util.py", pkg + ".pointnet_util", pkg)
+    ppta = _load("models/openshape/ppta.py", pkg + ".ppta", pkg)
+    return pu, ppta
+
+
 def uni3d_point_encoder():
     """models/point_encoder.py with pointnet2_ops stubbed (its fps() is NOT runnable: un-vendored CUDA)."""
     install_stubs()

@@ -28,6 +28,8 @@ def _load():
         _lib = C.CDLL(_SO)
         fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int64)
         _lib.oracle_fps.argtypes = [fp, C.c_int, C.c_int, C.c_int, C.c_int, ip, C.c_int, ip]
+        _lib.oracle_fps_pointnet2.argtypes = [fp, C.c_int, C.c_int, C.c_int, C.c_int, ip]
+        _lib.oracle_fps_pointnet2.restype = None
         _lib.oracle_knn.argtypes = [fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, ip, fp]
         _lib.oracle_ball.argtypes = [fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, ip]
         _lib.oracle_sqdist.argtypes = [fp, C.c_int, fp, C.c_int, fp]
@@ -61,6 +63,26 @@ def fps(xyz: np.ndarray, npoint: int, start_idx=None, skip_small_norm: bool = Fa
 
     def run(r):
         lib.oracle_fps(_fp(xyz), r[0], r[1], N, npoint, stp, int(skip_small_norm), _ip(out))
+
+    rs = _ranges(B, threads)
+    if len(rs) == 1:
+        run(rs[0])
+    else:
+        with ThreadPoolExecutor(len(rs)) as ex:
+            list(ex.map(run, rs))
+    return out
+
+
+def fps_pointnet2(xyz: np.ndarray, npoint: int, threads: int = 1) -> np.ndarray:
+    """The published pointnet2_ops furthest_point_sampling_kernel (Uni3D's FPS, models/point_encoder.py:7-14), thread by
+    thread: xyz (B,N,3) f32 -> indices (B,npoint) int64, first sample 0."""
+    lib = _load()
+    xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+    B, N, _ = xyz.shape
+    out = np.empty((B, npoint), dtype=np.int64)
+
+    def run(r):
+        lib.oracle_fps_pointnet2(_fp(xyz), r[0], r[1], N, npoint, _ip(out))
 
     rs = _ranges(B, threads)
     if len(rs) == 1:
@@ -135,10 +157,10 @@ def gather(xyz: np.ndarray, idx: np.ndarray) -> np.ndarray:
 
 
 def group_knn(xyz: np.ndarray, npoint: int, k: int, rgb=None, start_idx=None, skip_small_norm=False, threads: int = 1,
-              sort_by_index: bool = False):
+              sort_by_index: bool = False, pointnet2: bool = False):
     """Group.forward (point_encoder.py:99-127 / dvae.py:159-181): returns dict(fps_idx, center, idx, neigh[, feat]).
     Neighbours nearest-first, or in ascending point index (the CUDA kernel's emission order) if sort_by_index."""
-    fidx = fps(xyz, npoint, start_idx, skip_small_norm, threads)
+    fidx = fps_pointnet2(xyz, npoint, threads) if pointnet2 else fps(xyz, npoint, start_idx, skip_small_norm, threads)
     center = gather(xyz, fidx)
     idx = knn(xyz, center, k, threads)
     if sort_by_index:

@@ -5,7 +5,14 @@
  * Plain-C restatement of the reference's tokenizer arithmetic (paths relative to the reference repo):
  *   oracle_fps        models/ulip/pointbert/misc.py:40-60 fps(), models/openshape/pointnet_util.py:64-86
  *                     farthest_point_sample(); with start index 0 it also stands for models/point_encoder.py:7-14
- *                     (pointnet2_ops.furthest_point_sample, un-vendored CUDA: parity unpinned for that variant).
+ *                     (pointnet2_ops.furthest_point_sample, un-vendored CUDA) in torch arithmetic.
+ *   oracle_fps_pointnet2  the PUBLISHED algorithm of that un-vendored dependency (erikwijmans/Pointnet2_PyTorch,
+ *                     pointnet2_ops_lib 3.0.0, _ext-src/src/sampling_gpu.cu furthest_point_sampling_kernel +
+ *                     sampling.cpp: temp = 1e10, first sample 0), call site models/point_encoder.py:7-14: strided point
+ *                     ownership, per-thread strict '>' scan, pairwise tree reduction keeping the LEFT operand on ties,
+ *                     distances with the FMA contraction nvcc applies to the upstream expression (probed with nvcc
+ *                     12.9, oracle/pointnet2_contraction_probe.cu), '|p|^2 <= 1e-3' evaluated in double. The upstream
+ *                     binary cannot run here (parity unpinned against it); this pins the kernel to the published source.
  *   oracle_sqdist     square_distance(): models/point_encoder.py:30-49, dvae.py:130-149, pointnet_util.py:20-41
  *   oracle_knn        knn_point(): models/point_encoder.py:17-28, dvae.py:116-127  (topk largest=False)
  *   oracle_ball       query_ball_point(): models/openshape/pointnet_util.py:89-110
@@ -67,6 +74,61 @@ void oracle_fps(const float* xyz, int b0, int b1, int N, int G, const int64_t* s
     free(dist);
     free(skip);
   }
+}
+
+/* pointnet2_ops furthest_point_sampling_kernel<block_size> restated thread by thread.
+ * block_size = opt_n_threads(N): the largest power of two <= N, clipped to [1, 512] (cuda_utils.h). */
+static int pn2_block_size(int n) {
+  int p = 1;
+  while (p * 2 <= n && p * 2 <= 512) p *= 2;
+  return p;
+}
+
+void oracle_fps_pointnet2(const float* xyz, int b0, int b1, int N, int G, int64_t* out_idx) {
+  const int bs = pn2_block_size(N);
+  float* dists = (float*)malloc(sizeof(float) * (size_t)bs);
+  int* dists_i = (int*)malloc(sizeof(int) * (size_t)bs);
+  float* temp = (float*)malloc(sizeof(float) * (size_t)N);
+  for (int b = b0; b < b1; ++b) {
+    const float* dataset = xyz + (size_t)b * N * 3;
+    for (int p = 0; p < N; ++p) temp[p] = 1e10f;            /* sampling.cpp: torch::full({B, N}, 1e10) */
+    int old = 0;
+    out_idx[(size_t)b * G] = 0;
+    for (int j = 1; j < G; ++j) {
+      const float x1 = dataset[old * 3 + 0], y1 = dataset[old * 3 + 1], z1 = dataset[old * 3 + 2];
+      for (int tid = 0; tid < bs; ++tid) {
+        int besti = 0;
+        float best = -1.0f;
+        for (int k = tid; k < N; k += bs) {
+          const float x2 = dataset[k * 3 + 0], y2 = dataset[k * 3 + 1], z2 = dataset[k * 3 + 2];
+          /* nvcc: mag = fma(z2,z2, fma(x2,x2, y2*y2)); compared in double against 1e-3 */
+          const float mag = fmaf(z2, z2, fmaf(x2, x2, y2 * y2));
+          if ((double)mag <= 1e-3) continue;
+          const float dx = x2 - x1, dy = y2 - y1, dz = z2 - z1;
+          const float d = fmaf(dz, dz, fmaf(dx, dx, dy * dy));   /* nvcc's contraction of the upstream sum */
+          const float d2 = d < temp[k] ? d : temp[k];
+          temp[k] = d2;
+          besti = d2 > best ? k : besti;
+          best = d2 > best ? d2 : best;
+        }
+        dists[tid] = best;
+        dists_i[tid] = besti;
+      }
+      for (int half = bs / 2; half >= 1; half /= 2) {         /* __update(dists, dists_i, tid, tid + half) */
+        for (int tid = 0; tid < half; ++tid) {
+          const float v1 = dists[tid], v2 = dists[tid + half];
+          const int i1 = dists_i[tid], i2 = dists_i[tid + half];
+          dists[tid] = v1 > v2 ? v1 : v2;
+          dists_i[tid] = v2 > v1 ? i2 : i1;
+        }
+      }
+      old = dists_i[0];
+      out_idx[(size_t)b * G + j] = old;
+    }
+  }
+  free(dists);
+  free(dists_i);
+  free(temp);
 }
 
 /* full (G,N) matrix for one cloud, for spot checks */

@@ -121,7 +121,8 @@ def test_mode_dota_b64_golden_general_kernel(cuda_device):
 
 
 @pytest.mark.parametrize("S,K,M,D,Bp,B", [(1, 55, 8, 1024, 1, 64), (2, 9, 4, 512, 0, 16), (1, 15, 8, 1280, 32, 32),
-                                           (2, 7, 8, 384, 3, 9), (1, 216, 8, 1024, 64, 64), (1, 5, 4, 128, 1, 160 - 1)])
+                                           (2, 7, 8, 384, 3, 9), (1, 216, 8, 1024, 64, 64), (1, 5, 4, 128, 1, 160 - 1),
+                                           (1, 6, 8, 1152, 2, 8), (1, 4, 4, 3072, 1, 12)])   # slices of 384 columns (> one CTA)
 def test_mode_dota_batched_and_general_kernels_vs_oracle(S, K, M, D, Bp, B, cuda_device):
     """Cluster-per-class batched kernel (D split over the CTAs of a cluster, partials through distributed shared
     memory) and the general one-CTA-per-class kernel on identical inputs, both against the CPU oracle after two fits.
@@ -156,6 +157,7 @@ def test_mode_dota_batched_and_general_kernels_vs_oracle(S, K, M, D, Bp, B, cuda
         sens_lo = max(sens_lo, float(np.abs(los[0] - los[1]).max()))
     base = state_tol(dict(B=B, D=D))
     tol = {k_: base.get(k_, 1e-5) + 3.0 * sens[k_] for k_ in keys}
+    tol["pi"] = max(tol["pi"], tol["c"])      # pi = c / sum_m c with sum_m c >= 1: it cannot be tighter than c itself
     X, XP, G_ = x_fit.to(dev).contiguous(), x_pred.to(dev).contiguous(), gam.to(dev).contiguous()
     launches = {}
     for mode in (0, -1):

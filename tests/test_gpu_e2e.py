@@ -53,36 +53,43 @@ def test_core_loop_vs_reference_loop(name, tensor_cores, cuda_device):
         pass
 
 
-def replay_rng(T, N):
-    """The start indices / noise a CPU run of the reference draws (randint, randn_like, randint per step)."""
+def replay_rng(T, N, dota=False):
+    """The start indices / noise a CPU run of the reference draws: randint, randn_like, randint per step in the MODE-DOTA
+    branch (two encoder passes); one randint per step in the DOTA branch (one pass, no augmented view)."""
     torch.manual_seed(cases.E2E_LOOP_SEED)
     seq = []
     for _ in range(T):
         s0 = torch.randint(0, N, (1,), dtype=torch.long)
+        if dota:
+            seq.append((s0, None, None))
+            continue
         noise = torch.randn(1, N, 3)
         s1 = torch.randint(0, N, (1,), dtype=torch.long)
         seq.append((s0, noise, s1))
     return seq
 
 
+@pytest.mark.parametrize("use_graph", [True, False])
 @pytest.mark.parametrize("batch_views", [True, False])
 @pytest.mark.parametrize("name", ["e2e_ulip_d2_modedota_res", "e2e_ulip_d2_modedota"])
-def test_stream_engine_vs_reference_loop(name, batch_views, cuda_device):
+def test_stream_engine_vs_reference_loop(name, batch_views, use_graph, cuda_device):
     """The lock-step engine (stacked state, multi-text head, two-GEMM residual learning) on 3 streams fed the same
     stream: every stream must reproduce the reference loop, whether the sample and its jittered view go through the
-    encoder as one batch of 2S clouds (default) or one after the other (the reference's order)."""
+    encoder as one batch of 2S clouds (default) or one after the other (the reference's order) -- and as the captured
+    CUDA graph bench.py times (``use_graph``: steps >= 2 are graph replays; the FPS start indices and jitter noise of
+    the reference's CPU run arrive through the static buffers the graph reads)."""
     from uniadapter_b200.engine import StreamEngine
     inp = cases.e2e_inputs(name)
     gold = load_golden(name, inp)
     dev = cuda_device
     S = 3
     eng = StreamEngine(build(inp, dev, tensor_cores=True), 'ulip', torch.from_numpy(inp["text"]), S, inp["N"], cases.CFG,
-                       mode_M=inp["M"], res_learning=inp["res_learning"], device=dev, use_graph=False,
-                       batch_views=batch_views)
+                       mode_M=inp["M"], res_learning=inp["res_learning"], device=dev, use_graph=use_graph,
+                       batch_views=batch_views, external_rng=True)
     pcs = torch.from_numpy(inp["pc"])
     for i, (s0, noise, s1) in enumerate(replay_rng(inp["T"], inp["N"])):
-        eng.inject = dict(start=s0.expand(S).contiguous().to(dev), noise=noise.expand(S, -1, -1).contiguous().to(dev),
-                          start_aug=s1.expand(S).contiguous().to(dev))
+        eng.set_rng(s0.expand(S).contiguous().to(dev), s1.expand(S).contiguous().to(dev),
+                    noise.expand(S, -1, -1).contiguous().to(dev))
         final, pred = eng.step(pcs[i:i + 1].expand(S, -1, -1).contiguous().pin_memory())
         for s in range(S):
             assert int(pred[s]) == int(gold["pred"][i]), f"step {i} stream {s}"
@@ -90,6 +97,153 @@ def test_stream_engine_vs_reference_loop(name, batch_views, cuda_device):
     # closed form of the soft counts: every fit adds exactly B = 1
     csum = eng.adapter.c.sum(dim=(1, 2)).cpu().numpy()
     np.testing.assert_allclose(csum, inp["K"] + 2 * inp["T"], rtol=1e-5)
+    assert (eng.graph is not None) == use_graph
+
+
+class _ListDataset:
+    def __init__(self, pcs, rgbs=None):
+        self.pcs, self.rgbs = pcs, rgbs
+
+    def __len__(self):
+        return self.pcs.shape[0]
+
+    def __getitem__(self, i):
+        rgb = self.rgbs[i] if self.rgbs is not None else torch.ones_like(self.pcs[i])
+        return self.pcs[i], 0, "x", rgb
+
+
+@pytest.mark.parametrize("name", list(cases.E2E))
+def test_lockstep_cli_path_vs_reference_loop(name, cuda_device):
+    """``adapter.test_zeroshot_3d_lockstep`` -- what ``main_test-time.py`` runs by default -- against the reference's
+    loop: MODE-DOTA (with / without residual learning) through StreamEngine and the DOTA branch through DotaEngine, both
+    as captured CUDA graphs. Predictions bit-exact; MODE-DOTA logits at the stated fp32 tolerance; DOTA logits at the
+    fp16 tolerance of the unit test (4e-3 of the largest score) with the reference's Lambda of every step injected
+    (Lambda from another inverse routine differs at fp16 level), and the engine's own Lambda, computed by the
+    cooperative SPD inverse inside the graph, within 2e-2 of max|Lambda| of the reference's."""
+    from uniadapter_b200.adapter import test_zeroshot_3d_lockstep as lockstep
+    inp = cases.e2e_inputs(name)
+    gold = load_golden(name, inp)
+    dev = cuda_device
+    model = build(inp, dev, tensor_cores=True)
+    args = make_args(inp, dev)
+    args.npoints, args.seed = inp["N"], 42
+    rng = replay_rng(inp["T"], inp["N"], dota=inp["M"] == 0)
+    lam_feed = [torch.from_numpy(gold["Lambda"][i]) for i in range(inp["T"])] if inp["M"] == 0 else None
+    out = lockstep([_ListDataset(torch.from_numpy(inp["pc"]))], model, args, rng_feed=rng, lambda_feed=lam_feed)[0]
+    np.testing.assert_array_equal(out["preds"].numpy(), gold["pred"])
+    ref = gold["final_logits"]
+    if inp["M"] > 0:
+        np.testing.assert_allclose(out["logits"].numpy(), ref, **e2e_tolerances(name)["final"])
+    else:
+        np.testing.assert_allclose(out["logits"].numpy(), ref, rtol=4e-3, atol=4e-3 * np.abs(ref).max())
+        eng = out["engine"]
+        lam_ref = gold["Lambda"][-1].astype(np.float32)
+        np.testing.assert_allclose(eng.own_lambda.float().cpu().numpy(), lam_ref, rtol=0, atol=2e-2 * np.abs(lam_ref).max())
+        np.testing.assert_allclose(torch.diagonal(eng.adapter.overall_Sigma).cpu().numpy(), gold["overall_diag"][-1],
+                                   rtol=1e-4, atol=1e-9)
+        np.testing.assert_allclose(eng.adapter.mu.cpu().numpy(), gold["mu"], rtol=1e-4, atol=4e-6)   # 1e-4 of the feature scale (unit rows, D = 512)
+        np.testing.assert_allclose(eng.adapter.c.cpu().numpy(), gold["c"], rtol=1e-4)
+    assert out["engine"].graph is not None
+
+
+@pytest.mark.parametrize("path", ["core", "engine_graph"])
+@pytest.mark.parametrize("name", list(cases.E2E_OSHAPE))
+def test_openshape_loop_vs_reference_loop(name, path, cuda_device):
+    """cfg 3 end to end: OpenShape PPAT (FPS + ball query over 10 000 coloured points) + MODE-DOTA M=8, K=15, D=1280,
+    against the reference's own ppta.py / pointnet_util.py / DOTA_mix loop: through the drop-in per-sample loop and
+    through the lock-step engine as a captured graph (3 identical streams)."""
+    from uniadapter_b200.encoders import OpenShapePPAT
+    inp = cases.e2e_oshape_inputs(name)
+    gold = load_golden(name, inp)
+    dev = cuda_device
+    torch.manual_seed(cases.E2E_MODEL_SEED)
+    model = OpenShapePPAT(depth=inp["depth"], patches=inp["S"]).to(dev).eval()
+    pcs, rgbs = torch.from_numpy(inp["pc"]), torch.from_numpy(inp["rgb"])
+    tol = e2e_tolerances(name)["final"]
+    if path == "core":
+        from uniadapter_b200.adapter import test_zeroshot_3d_core as core
+        einp = dict(M=inp["M"], res_learning=False, text=inp["text"])
+        args = make_args(einp, dev)
+        args.vlm3d = 'openshape'
+        loader = [(pcs[i:i + 1], torch.tensor([0]), ["x"], rgbs[i:i + 1]) for i in range(inp["T"])]
+        torch.manual_seed(cases.E2E_LOOP_SEED)
+        out = core(loader, "synthetic", model, None, None, args, None)
+        np.testing.assert_array_equal(out["preds"].numpy(), gold["pred"])
+        np.testing.assert_allclose(out["logits"].numpy(), gold["final_logits"], **tol)
+        np.testing.assert_allclose(out["adapter"].c.cpu().numpy(), gold["c"], rtol=1e-4, atol=2e-4)
+        np.testing.assert_allclose(out["adapter"].mu.cpu().numpy()[:, :, ::8], gold["mu_sample"], rtol=1e-4, atol=1e-5)
+        return
+    from uniadapter_b200.engine import StreamEngine
+    S = 3
+    eng = StreamEngine(model, 'openshape', torch.from_numpy(inp["text"]), S, inp["N"], cases.CFG, mode_M=inp["M"],
+                       res_learning=False, device=dev, use_graph=True, external_rng=True)
+    for i, (s0, noise, s1) in enumerate(replay_rng(inp["T"], inp["N"])):
+        eng.set_rng(s0.expand(S).contiguous().to(dev), s1.expand(S).contiguous().to(dev),
+                    noise.expand(S, -1, -1).contiguous().to(dev))
+        final, pred = eng.step(pcs[i:i + 1].expand(S, -1, -1).contiguous().pin_memory(),
+                               rgbs[i:i + 1].expand(S, -1, -1).contiguous().pin_memory())
+        for s in range(S):
+            assert int(pred[s]) == int(gold["pred"][i]), f"step {i} stream {s}"
+            np.testing.assert_allclose(final[s].numpy(), gold["final_logits"][i], **tol)
+    assert eng.graph is not None
+
+
+@pytest.mark.parametrize("tensor_cores", [False, True])
+@pytest.mark.parametrize("name", list(cases.UNI3D_FRONT))
+def test_uni3d_front_vs_reference(name, tensor_cores, cuda_device):
+    """cfg 4/5 geometry: Uni3D tokenizer (pointnet2_ops FPS arithmetic, kNN 64, colour concat) + mini-PointNet +
+    encoder2trans + position embedding against the reference's Group / Encoder / PointcloudEncoder front end
+    (golden: oracle.make_golden uni3d_front; groups tied exactly at the k-th distance have no unique reference answer)."""
+    from test_e2e_oracle import uni3d_untied_tokens
+    from uniadapter_b200.encoders import Uni3DEncoder, use_tensor_cores
+    inp = cases.uni3d_front_inputs(name)
+    gold = load_golden(name, inp)
+    torch.manual_seed(cases.E2E_MODEL_SEED)
+    enc = Uni3DEncoder(depth=0).to(cuda_device).eval()
+    if tensor_cores:
+        use_tensor_cores(enc, True)
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False        # the plain torch path would run its 1x1 convolutions in single-pass TF32
+    try:
+        with torch.no_grad():
+            x = enc.front(torch.from_numpy(inp["xyz"]).to(cuda_device), torch.from_numpy(inp["rgb"]).to(cuda_device)).cpu().numpy()
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    keep = uni3d_untied_tokens(inp)
+    np.testing.assert_allclose(x[:, :, ::8][keep], gold["x_pre_sample"][keep], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(x.astype(np.float64).sum(-1)[keep], gold["x_pre_rowsum"][keep], rtol=1e-4, atol=2e-3)
+    _, center = enc.group_divider(torch.from_numpy(inp["xyz"]).to(cuda_device), torch.from_numpy(inp["rgb"]).to(cuda_device))[:2]
+    np.testing.assert_array_equal(center.cpu().numpy(), gold["center"])
+
+
+def test_stream_results_do_not_depend_on_the_partition(cuda_device):
+    """stream s draws its jitter and FPS starts from the generator keyed by seed + s, so running streams
+    {0,1,2,3} in one engine, or {0,2} and {1,3} in two (two ranks), gives every stream the same predictions and logits."""
+    from uniadapter_b200.engine import StreamEngine
+    from uniadapter_b200.streams import unit_sphere_clouds
+    inp = cases.e2e_inputs("e2e_ulip_d2_modedota_res")
+    dev = cuda_device
+    model = build(inp, dev, tensor_cores=True)
+    text = torch.from_numpy(inp["text"])
+    T = 5
+    clouds = [unit_sphere_clouds(T, inp["N"], torch.Generator().manual_seed(100 + s)) for s in range(4)]
+
+    def run(ids):
+        eng = StreamEngine(model, 'ulip', text, len(ids), inp["N"], cases.CFG, mode_M=8, res_learning=True, device=dev,
+                           use_graph=True, seed=7, stream_ids=ids)
+        outs = []
+        for i in range(T):
+            final, _ = eng.step(torch.stack([clouds[s][i] for s in ids]).pin_memory())
+            outs.append(final.clone())
+        return torch.stack(outs, 1)            # (len(ids), T, K)
+
+    whole = run([0, 1, 2, 3])
+    even, odd = run([0, 2]), run([1, 3])
+    # same draws, same arithmetic per cloud; library GEMMs of the torch layers may pick another kernel at another batch
+    for a, b in ((whole[0], even[0]), (whole[2], even[1]), (whole[1], odd[0]), (whole[3], odd[1])):
+        assert torch.equal(a.argmax(-1), b.argmax(-1))
+        np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=1e-4, atol=1e-3)
+    assert not torch.allclose(whole[0], whole[1], rtol=1e-2, atol=1e-1)
 
 
 def test_stream_engine_cuda_graph(cuda_device):

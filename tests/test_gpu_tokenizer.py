@@ -167,7 +167,7 @@ def test_uni3d_entry_points_and_skip_small_norm(cuda_device):
     xyz = cu(xyz_np, cuda_device)
     idx = ua.furthest_point_sample(xyz, 64)
     assert idx.dtype == torch.int32 and tuple(idx.shape) == (3, 64)
-    np.testing.assert_array_equal(idx.cpu().numpy().astype(np.int64), T.fps(xyz_np, 64, None))
+    np.testing.assert_array_equal(idx.cpu().numpy().astype(np.int64), T.fps_pointnet2(xyz_np, 64))
     g = ua.gather_operation(xyz.transpose(1, 2).contiguous(), idx).transpose(1, 2).contiguous()
     np.testing.assert_array_equal(g.cpu().numpy(), T.gather(xyz_np, idx.cpu().numpy().astype(np.int64)))
     np.testing.assert_array_equal(ua.fps_uni3d(xyz, 64).cpu().numpy(), g.cpu().numpy())
@@ -200,3 +200,55 @@ def test_argument_errors(cuda_device):
     with pytest.raises(ua._lib.UaError):
         ua.knn_group(xyz.expand(1, 16, 3)[:, ::2], xyz[:, :4].contiguous(), 200) if False else ua.knn_group(
             torch.zeros(1, 300, 3, device=cuda_device), xyz[:, :4].contiguous(), 200)   # k > 128 unsupported
+
+
+@pytest.mark.parametrize("B,N,G,kind", [(3, 1024, 512, "plain"), (1, 10000, 512, "plain"), (2, 300, 64, "dups"),
+                                        (2, 33, 33, "plain"), (2, 500, 96, "clump"), (1, 64, 8, "all_skipped"),
+                                        (150, 1024, 64, "plain"), (1, 2048, 128, "dups"), (2, 4097, 40, "clump")])
+def test_fps_pointnet2_arithmetic_vs_published_algorithm(B, N, G, kind, cuda_device):
+    """Uni3D's FPS is the un-vendored pointnet2_ops CUDA kernel. ``pointnet2=True`` follows the published kernel
+    (FMA-contracted distances, near-origin points never take part, ties resolved like upstream's left-biased reduction tree);
+    oracle_fps_pointnet2 restates that kernel thread by thread. Register path and cluster path must both match it
+    bit for bit, including duplicated points (ties everywhere), a clump at the origin and a cloud with no candidate."""
+    import uniadapter_b200 as ua
+    from oracle import synth
+    from uniadapter_b200 import _lib
+    xyz_np = synth.cloud(B, N, 900 + N + G)
+    if kind == "dups":
+        third = N // 3
+        xyz_np[:, third:2 * third] = xyz_np[:, :third]
+        xyz_np[:, 2 * third:3 * third] = xyz_np[:, :third]
+    if kind == "clump":
+        xyz_np[:, : N // 5] *= np.float32(0.02)
+    if kind == "all_skipped":
+        xyz_np *= np.float32(0.01)
+    want = T.fps_pointnet2(xyz_np, G, threads=4)
+    xyz = cu(xyz_np, cuda_device)
+    for mode in (1, -1):            # cluster path forced on / off (it only engages for few large clouds)
+        _lib.set_tuning("fps_cluster", mode)
+        try:
+            idx, centers = ua.fps_sample(xyz, G, None, pointnet2=True)
+        finally:
+            _lib.set_tuning("fps_cluster", 0)
+        np.testing.assert_array_equal(idx.cpu().numpy(), want, err_msg=f"fps_cluster={mode}")
+        np.testing.assert_array_equal(centers.cpu().numpy(), T.gather(xyz_np, want))
+
+
+def test_fps_pointnet2_vs_torch_order_disagreement_on_cfg4_clouds(cuda_device):
+    """How far the two arithmetic variants of Uni3D's FPS drift apart on the cfg 4 shape (10 000 points, 512 samples):
+    the FMA contraction changes some distances by one ulp, so the selections differ in a few places; both variants are
+    exact against their own oracle. The counts are printed (pytest -s) and bounded loosely."""
+    import uniadapter_b200 as ua
+    from oracle import synth
+    xyz_np = synth.cloud(8, 10000, 2)
+    xyz = cu(xyz_np, cuda_device)
+    a, _ = ua.fps_sample(xyz, 512, None)
+    b, _ = ua.fps_sample(xyz, 512, None, pointnet2=True)
+    np.testing.assert_array_equal(a.cpu().numpy(), T.fps(xyz_np, 512, None, threads=4))
+    np.testing.assert_array_equal(b.cpu().numpy(), T.fps_pointnet2(xyz_np, 512, threads=4))
+    a, b = a.cpu().numpy(), b.cpu().numpy()
+    pos = (a != b).sum(axis=1)
+    sets = [len(set(a[i]) ^ set(b[i])) // 2 for i in range(8)]
+    print(f"pointnet2 vs torch-order FPS, 8 clouds x 10 000 points, 512 samples: positions differing {pos.tolist()}, "
+          f"samples not shared {sets}")
+    assert (a[:, :16] == b[:, :16]).all() and max(sets) < 256

@@ -39,6 +39,7 @@ SIGNATURES = {
     "ua_row_stats_f32": (_I, [_P, _I, _I, C.c_longlong, _P, _P, _P, _P]),
     "ua_modedota_step_f32": (_I, [_P, _I, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _I, _I, _P]),
     "ua_fuse_logits_f32": (_I, [_P, _P, _I, _I, _I, _P, _I, _I, _F, _F, _F, _F, _F, _I, _P, _P, _P, _P]),
+    "ua_stream_rng_f32": (_I, [_P, _P, _I, C.c_longlong, _P, _P, _I, _P, _P]),
     "ua_residual_scratch_floats": (C.c_longlong, [_I, _I, _I, _I]),
     "ua_residual_learn_f32": (_I, [_P, C.c_longlong, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, C.c_double,
                                     C.c_double, C.c_double, C.c_double, _I, _P, _P, _P, C.c_longlong, _P]),

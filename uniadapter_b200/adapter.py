@@ -142,7 +142,7 @@ def test_zeroshot_3d_core(test_loader, validate_dataset_name, model, clip_model,
             'logits': torch.cat(all_logits) if all_logits else None}
 
 
-def test_zeroshot_3d_lockstep(datasets, model, args, names=None):
+def test_zeroshot_3d_lockstep(datasets, model, args, names=None, rng_feed=None, lambda_feed=None):
     """The same per-sample adaptation loop for S independent corruption streams, advanced in lock-step on one GPU.
 
     The reference builds a fresh adapter per corruption and walks the corruptions one after the other
@@ -155,7 +155,12 @@ def test_zeroshot_3d_lockstep(datasets, model, args, names=None):
     MODE-DOTA (``--use-mode-dota``, with or without ``--res-learning``) for any number of streams; the DOTA branch
     (``--use-dota``) for one stream per call (``engine.DotaEngine``). Batch size 1, rgb = ones (what every dataset class
     of the reference returns). Returns one result dict per stream (acc1/acc3/acc5 in percent, preds) plus
-    the per-step device times (reference event placement: host->device copy to fused logits)."""
+    the per-step device times (reference event placement: host->device copy to fused logits).
+
+    Parity harness: ``rng_feed`` yields, per step, ``(start (S,), noise (S,N,3), start_aug (S,))`` -- the FPS start indices
+    and jitter noise a CPU run of the reference draws -- and ``lambda_feed`` (DOTA branch) the reference's Lambda after
+    that step; both land in static buffers of the engine, so the captured CUDA graph itself is compared with the
+    goldens. Without them every stream draws from its own counter-based device generator (seed + stream index)."""
     from .engine import DotaEngine, StreamEngine
     from .streams import PinnedPrefetcher
     device = torch.device(args.device)
@@ -166,10 +171,17 @@ def test_zeroshot_3d_lockstep(datasets, model, args, names=None):
         # the DOTA branch (full covariance): one stream per engine, the per-sample step as one CUDA-graph replay
         if S != 1:
             raise NotImplementedError("the DOTA branch runs one stream per engine (its covariance stack is per adapter)")
-        engine = DotaEngine(model, args.vlm3d, text, args.npoints, cfg, device=device, use_graph=True, seed=args.seed)
+        engine = DotaEngine(model, args.vlm3d, text, args.npoints, cfg, device=device, use_graph=True, seed=args.seed,
+                            stream_id=getattr(args, 'stream_ids', [0])[0], external_rng=rng_feed is not None,
+                            external_lambda=lambda_feed is not None)
     else:
         engine = StreamEngine(model, args.vlm3d, text, S, args.npoints, cfg, mode_M=args.mode_M,
-                              res_learning=bool(args.res_learning), device=device, use_graph=True, seed=args.seed)
+                              res_learning=bool(args.res_learning), device=device, use_graph=True, seed=args.seed,
+                              stream_ids=getattr(args, 'stream_ids', None), external_rng=rng_feed is not None)
+    rng_iter = iter(rng_feed) if rng_feed is not None else None
+    lam_iter = iter(lambda_feed) if lambda_feed is not None else None
+    keep_logits = bool(getattr(args, 'keep_logits', False))
+    all_logits = []
     colored = args.vlm3d == 'openshape' and args.use_mode_dota      # coloured streams: rgb travels with the cloud
     feed = PinnedPrefetcher(datasets, args.npoints, with_rgb=colored)
     hits = torch.zeros(S, 3)
@@ -178,6 +190,14 @@ def test_zeroshot_3d_lockstep(datasets, model, args, names=None):
     n = 0
     for item in feed:
         pc_host, labels = item[0], item[1]
+        if rng_iter is not None:
+            start, noise, start_aug = next(rng_iter)
+            if args.use_mode_dota:
+                engine.set_rng(start.to(device), start_aug.to(device), noise.to(device))
+            else:
+                engine.set_rng(start.to(device))
+        if lam_iter is not None:
+            engine.set_lambda(next(lam_iter).to(device))
         torch.cuda.synchronize()
         start_event.record()
         # (S,K) pinned host logits; synchronised on return
@@ -191,6 +211,8 @@ def test_zeroshot_3d_lockstep(datasets, model, args, names=None):
         hits[:, 1] += match[:, :3].any(1).float()
         hits[:, 2] += match[:, :5].any(1).float()
         preds.append(top[:, 0].clone())
+        if keep_logits:
+            all_logits.append(final.clone())
         n += 1
         if n % max(1, args.print_freq) == 0:
             logging.info(f"Test: [{n}/{feed.length}] Acc@1 {100 * float(hits[:, 0].mean()) / n:.2f} "
@@ -202,5 +224,6 @@ def test_zeroshot_3d_lockstep(datasets, model, args, names=None):
         out.append({'acc1': acc[0], 'acc3': acc[1], 'acc5': acc[2], 'preds': preds[s], 'times_ms': times,
                     'ms_per_sample': (sum(times) / max(n, 1)) / S,
                     'median_ms_per_sample': (sorted(times)[len(times) // 2] / S) if times else float('nan'),
-                    'name': names[s] if names else str(s)})
+                    'name': names[s] if names else str(s),
+                    'logits': torch.stack([l[s] for l in all_logits]) if all_logits else None, 'engine': engine})
     return out

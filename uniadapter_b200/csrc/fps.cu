@@ -5,7 +5,15 @@
 // Semantics follow models/ulip/pointbert/misc.py:40-60 and models/openshape/pointnet_util.py:64-86 of the
 // reference: dist = sum((xyz - centroid)**2, -1) rounded per operation, distance = min(distance, dist) from an
 // initial 1e10, farthest = first index of the maximum. The Uni3D path (models/point_encoder.py:7-14, un-vendored
-// pointnet2_ops CUDA) maps to start index 0 (+ optional skip of near-origin points).
+// pointnet2_ops CUDA) maps to start index 0 and has two arithmetic variants: the torch order above (+ optional skip of
+// near-origin points), and `PN2`, the published pointnet2_ops kernel's own arithmetic (furthest_point_sampling_kernel,
+// pointnet2_ops_lib 3.0.0): distances with the FMA contraction nvcc gives the upstream source,
+// d = fma(dz,dz, fma(dx,dx, dy*dy)), points with fma(z,z, fma(x,x, y*y)) <= 1e-3 (compared in double) never take part,
+// and ties follow upstream's reduction -- thread `k mod block_size` owns point k, scans its points with a strict '>',
+// and the pairwise tree keeps the left operand on ties, which favours the smallest bit-reversed thread id. Here
+// ownership is different (registers), so every candidate carries the permuted index
+// comp(k) = bitrev(k mod bs) * ceil(N / bs) + k / bs and ties take the lowest comp; bs = largest power of two
+// <= min(N, 512) as upstream's opt_n_threads.
 #include <cooperative_groups.h>
 #include "common.cuh"
 
@@ -19,6 +27,26 @@ int g_fps_cluster = 0;  // tuning: -1 disables the cluster path, N > 0 = smalles
 namespace {
 
 constexpr float kFpsInit = 1e10f;
+
+// pointnet2_ops tie order. Upstream thread t = k mod bs owns point k and keeps its FIRST maximum; the pairwise tree
+// (t, t + bs/2), (t, t + bs/4), ... (0, 1) keeps the LEFT operand on ties, so among equal maxima the winner is the thread
+// with the smallest BIT-REVERSED id (the last level lets even threads beat odd ones, the one before decides bit 1, ...):
+// comp(k) = bitrev_lg(k mod bs) * q + k / bs with bs = 2^lg, q = ceil(N / bs); ties go to the lowest comp.
+struct Pn2Order {
+  int lg, q;
+  __device__ __forceinline__ uint32_t rev(uint32_t t) const { return lg ? (__brev(t) >> (32 - lg)) : 0u; }
+  __device__ __forceinline__ uint32_t comp(uint32_t k) const { return rev(k & ((1u << lg) - 1u)) * (uint32_t)q + (k >> lg); }
+  __device__ __forceinline__ uint32_t index(uint32_t c) const { return ((c % (uint32_t)q) << lg) + rev(c / (uint32_t)q); }
+};
+__device__ __forceinline__ float sqdist_pn2(float px, float py, float pz, float cx, float cy, float cz) {
+  const float dx = __fsub_rn(px, cx), dy = __fsub_rn(py, cy), dz = __fsub_rn(pz, cz);
+  return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+}
+__device__ __forceinline__ bool pn2_skipped(float x, float y, float z) {
+  return (double)__fmaf_rn(z, z, __fmaf_rn(x, x, __fmul_rn(y, y))) <= 1e-3;
+}
+// block / warp keys: 0 = no candidate (every owned point skipped), else distance bits + 1 (distances are >= 0)
+__device__ __forceinline__ uint32_t pn2_key(float best) { return best < 0.f ? 0u : __float_as_uint(best) + 1u; }
 
 __device__ __forceinline__ void block_argmax(uint32_t bits, uint32_t idx, uint2 (*s_red)[32], int buf, int lane,
                                              int warp, int nwarps, uint32_t& out_idx) {
@@ -52,10 +80,10 @@ __device__ __forceinline__ void write_selection(const int* s_sel, const float* c
 // Register-resident path: N <= PPT * blockDim.x, cloud also staged in shared memory for the centroid fetch.
 // (Measured and rejected: thread-blocked point ownership with ballot + find-first-set instead of the second REDUX of
 // each reduction level - 111 us instead of 91 us at N = 1024: REDUX.MIN is cheaper than vote + ffs + shuffle.)
-template <int PPT, typename IdxT>
+template <int PPT, typename IdxT, bool PN2>
 __global__ void __launch_bounds__(PPT == 12 ? 896 : 1024, 1)
     fps_reg_kernel(const float* __restrict__ xyz, int N, int G, const long long* __restrict__ start_idx,
-                   int skip_small, IdxT* __restrict__ out_idx, float* __restrict__ out_centers) {
+                   int skip_small, Pn2Order ord, IdxT* __restrict__ out_idx, float* __restrict__ out_centers) {
   extern __shared__ __align__(16) float s_dyn[];
   float* s_xyz = s_dyn;                              // [3N]
   int* s_sel = reinterpret_cast<int*>(s_dyn + 3 * N);  // [G]
@@ -78,9 +106,15 @@ __global__ void __launch_bounds__(PPT == 12 ? 896 : 1024, 1)
     px[j] = valid ? s_xyz[3 * p + 0] : 0.f;
     py[j] = valid ? s_xyz[3 * p + 1] : 0.f;
     pz[j] = valid ? s_xyz[3 * p + 2] : 0.f;
-    if (skip_small && valid) valid = sqnorm_nofma(px[j], py[j], pz[j]) > 1e-3f;
-    // an excluded slot keeps distance 0 forever: it can only tie with exhausted points, and then loses on index
-    dmin[j] = valid ? kFpsInit : 0.f;
+    if (PN2) {
+      // a point that never takes part keeps the running "distance" -1 (fminf(-1, d) = -1 < any candidate)
+      if (valid) valid = !pn2_skipped(px[j], py[j], pz[j]);
+      dmin[j] = valid ? kFpsInit : -1.f;
+    } else {
+      if (skip_small && valid) valid = sqnorm_nofma(px[j], py[j], pz[j]) > 1e-3f;
+      // an excluded slot keeps distance 0 forever: it can only tie with exhausted points, and then loses on index
+      dmin[j] = valid ? kFpsInit : 0.f;
+    }
   }
 
   long long s0 = start_idx ? start_idx[b] : 0;
@@ -93,18 +127,44 @@ __global__ void __launch_bounds__(PPT == 12 ? 896 : 1024, 1)
     if (i == G - 1) break;
     const float cx = s_xyz[3 * cur + 0], cy = s_xyz[3 * cur + 1], cz = s_xyz[3 * cur + 2];
     float best = -1.f;
-    int bestj = 0;
+    if (PN2) {
+      int bestj = 0;
+      bool tie = false;
 #pragma unroll
-    for (int j = 0; j < PPT; ++j) {
-      const float d = sqdist_nofma(px[j], py[j], pz[j], cx, cy, cz);
-      const float dm = fminf(dmin[j], d);
-      dmin[j] = dm;
-      if (dm > best) {
-        best = dm;
-        bestj = j;
+      for (int j = 0; j < PPT; ++j) {
+        const float d = sqdist_pn2(px[j], py[j], pz[j], cx, cy, cz);
+        const float dm = fminf(dmin[j], d);
+        dmin[j] = dm;
+        tie |= dm == best;
+        if (dm > best) {
+          best = dm;
+          bestj = j;
+          tie = false;
+        }
       }
+      uint32_t bestc = best < 0.f ? 0u : ord.comp((uint32_t)(bestj * T + tid));
+      if (__any_sync(kFullMask, tie && best >= 0.f)) {     // rare: several of a thread's points share its maximum
+#pragma unroll
+        for (int j = 0; j < PPT; ++j)
+          if (dmin[j] == best && best >= 0.f) bestc = min(bestc, ord.comp((uint32_t)(j * T + tid)));
+      }
+      uint32_t win;
+      block_argmax(pn2_key(best), bestc, s_red, i & 1, lane, warp, nwarps, win);
+      cur = ord.index(win);      // nobody has a candidate: every thread reports comp 0 = point 0, as upstream
+    } else {
+      int bestj = 0;
+#pragma unroll
+      for (int j = 0; j < PPT; ++j) {
+        const float d = sqdist_nofma(px[j], py[j], pz[j], cx, cy, cz);
+        const float dm = fminf(dmin[j], d);
+        dmin[j] = dm;
+        if (dm > best) {
+          best = dm;
+          bestj = j;
+        }
+      }
+      block_argmax(__float_as_uint(best), (uint32_t)(bestj * T + tid), s_red, i & 1, lane, warp, nwarps, cur);
     }
-    block_argmax(__float_as_uint(best), (uint32_t)(bestj * T + tid), s_red, i & 1, lane, warp, nwarps, cur);
   }
   write_selection<IdxT>(s_sel, s_xyz, nullptr, b, G, out_idx, out_centers);
 }
@@ -127,10 +187,10 @@ __global__ void __launch_bounds__(PPT == 12 ? 896 : 1024, 1)
 // protocol 305 us (319 us when every warp polls; 485 us when every warp publishes and 80 slots are polled).
 constexpr int kFpsClusterPpt = 4;
 
-template <typename IdxT>
+template <typename IdxT, bool PN2>
 __global__ void __launch_bounds__(512, 1)
     fps_cluster_kernel(const float* __restrict__ xyz, int N, int G, int chunk, const long long* __restrict__ start_idx,
-                       int skip_small, IdxT* __restrict__ out_idx, float* __restrict__ out_centers) {
+                       int skip_small, Pn2Order ord, IdxT* __restrict__ out_idx, float* __restrict__ out_centers) {
   constexpr int PPT = kFpsClusterPpt;
   extern __shared__ __align__(16) float s_dyn[];
   cg::cluster_group cluster = cg::this_cluster();
@@ -158,8 +218,13 @@ __global__ void __launch_bounds__(512, 1)
     px[j] = valid ? s_xyz[3 * (n0 + p) + 0] : 0.f;
     py[j] = valid ? s_xyz[3 * (n0 + p) + 1] : 0.f;
     pz[j] = valid ? s_xyz[3 * (n0 + p) + 2] : 0.f;
-    if (skip_small && valid) valid = sqnorm_nofma(px[j], py[j], pz[j]) > 1e-3f;
-    dmin[j] = valid ? kFpsInit : 0.f;
+    if (PN2) {
+      if (valid) valid = !pn2_skipped(px[j], py[j], pz[j]);
+      dmin[j] = valid ? kFpsInit : -1.f;
+    } else {
+      if (skip_small && valid) valid = sqnorm_nofma(px[j], py[j], pz[j]) > 1e-3f;
+      dmin[j] = valid ? kFpsInit : 0.f;
+    }
   }
 
   long long s0 = start_idx ? start_idx[b] : 0;
@@ -176,39 +241,70 @@ __global__ void __launch_bounds__(512, 1)
     if (i == G - 1) break;
     const float cx = s_xyz[3 * cur + 0], cy = s_xyz[3 * cur + 1], cz = s_xyz[3 * cur + 2];
     float best = -1.f;
-    int bestj = 0;
+    uint32_t bits, cand;           // this thread's candidate: key (distance bits) and tie-order word
+    if (PN2) {
+      int bestj = 0;
+      bool tie = false;
 #pragma unroll
-    for (int j = 0; j < PPT; ++j) {
-      const float d = sqdist_nofma(px[j], py[j], pz[j], cx, cy, cz);
-      const float dm = fminf(dmin[j], d);
-      dmin[j] = dm;
-      if (dm > best) {
-        best = dm;
-        bestj = j;
+      for (int j = 0; j < PPT; ++j) {
+        const float d = sqdist_pn2(px[j], py[j], pz[j], cx, cy, cz);
+        const float dm = fminf(dmin[j], d);
+        dmin[j] = dm;
+        tie |= dm == best;
+        if (dm > best) {
+          best = dm;
+          bestj = j;
+          tie = false;
+        }
       }
+      uint32_t bestc = best < 0.f ? 0u : ord.comp((uint32_t)(n0 + bestj * T + tid));
+      if (__any_sync(kFullMask, tie && best >= 0.f)) {     // rare: several of a thread's points share its maximum
+#pragma unroll
+        for (int j = 0; j < PPT; ++j)
+          if (dmin[j] == best && best >= 0.f) bestc = min(bestc, ord.comp((uint32_t)(n0 + j * T + tid)));
+      }
+      bits = pn2_key(best), cand = bestc;
+    } else {
+      int bestj = 0;
+#pragma unroll
+      for (int j = 0; j < PPT; ++j) {
+        const float d = sqdist_nofma(px[j], py[j], pz[j], cx, cy, cz);
+        const float dm = fminf(dmin[j], d);
+        dmin[j] = dm;
+        if (dm > best) {
+          best = dm;
+          bestj = j;
+        }
+      }
+      bits = __float_as_uint(best), cand = (uint32_t)(bestj * T + tid);
     }
-    // slice-local argmax (lowest local index among the maxima); out-of-range slots hold distance 0 and the highest indices
+    // slice-local argmax (lowest tie-order word among the maxima); out-of-range slots of the torch-order variant hold
+    // distance 0 and the highest local indices
     const int par = i & 1;
-    const uint32_t bits = __float_as_uint(best);
     const uint32_t wmax = __reduce_max_sync(kFullMask, bits);
-    const uint32_t widx = __reduce_min_sync(kFullMask, bits == wmax ? (uint32_t)(bestj * T + tid) : 0xffffffffu);
+    const uint32_t widx = __reduce_min_sync(kFullMask, bits == wmax ? cand : 0xffffffffu);
     if (lane == 0) s_red[par][warp] = make_uint2(wmax, widx);
     __syncthreads();
     if (warp == 0) {
-      // publish into THIS CTA's slot: tag | distance bits (low word), global index (high word); empty slice: distance 0
+      // publish into THIS CTA's slot: tag | key (low word), tie-order word (high word); empty slice: key 0
       const uint32_t tag = (((uint32_t)i >> 1) & 1u) ^ 1u;       // flips on every reuse of parity slot `par`
       const uint2 v = lane < nwarps ? s_red[par][lane] : make_uint2(0u, 0xffffffffu);
       const uint32_t bmax = __reduce_max_sync(kFullMask, v.x);
       const uint32_t lidx = __reduce_min_sync(kFullMask, v.x == bmax ? v.y : 0xffffffffu);
       if (lane == 0) {
-        const bool has = (int)lidx < nl;
-        const uint32_t lo = (has ? bmax : 0u) | (tag << 31);
-        const uint32_t hi = has ? (uint32_t)n0 + lidx : 0xffffffffu;
+        uint32_t lo, hi;
+        if (PN2) {
+          lo = bmax | (tag << 31), hi = lidx;                    // key 0 <-> comp 0 (point 0), as upstream
+        } else {
+          const bool has = (int)lidx < nl;
+          lo = (has ? bmax : 0u) | (tag << 31);
+          hi = has ? (uint32_t)n0 + lidx : 0xffffffffu;
+        }
         const unsigned long long word = ((unsigned long long)hi << 32) | lo;
         asm volatile("st.volatile.shared.b64 [%0], %1;" ::"r"(smem_u32(&s_mine[par])), "l"(word) : "memory");
       }
       // collect (pull): lane r < C polls CTA r's slot through distributed shared memory until it carries this
-      // iteration's tag; warp maximum of the distance bits, lowest rank among the maxima (= lowest index).
+      // iteration's tag; warp maximum of the keys, lowest tie-order word among the maxima.
       // Only this warp polls: more pollers only slow the peers' shared-memory ports down (measured).
       uint32_t cb = 0, hi = 0xffffffffu;
       if (lane < C) {
@@ -221,12 +317,11 @@ __global__ void __launch_bounds__(512, 1)
       }
       __syncwarp();
       const uint32_t gmax = __reduce_max_sync(kFullMask, cb);
-      const unsigned mwin = __ballot_sync(kFullMask, lane < C && cb == gmax);
-      const uint32_t g = __shfl_sync(kFullMask, hi, __ffs(mwin) - 1);
+      const uint32_t g = __reduce_min_sync(kFullMask, (lane < C && cb == gmax) ? hi : 0xffffffffu);
       if (lane == 0) s_cur[par] = g;
     }
     __syncthreads();
-    const uint32_t gidx = s_cur[par];
+    const uint32_t gidx = PN2 ? ord.index(s_cur[par]) : s_cur[par];
     cur = gidx < (uint32_t)N ? gidx : 0u;     // (all slices empty cannot happen: N >= 1)
   }
   if (rank == 0) write_selection<IdxT>(s_sel, s_xyz, nullptr, b, G, out_idx, out_centers);   // every CTA holds the same list
@@ -277,11 +372,11 @@ __global__ void __launch_bounds__(1024, 1)
   write_selection<IdxT>(s_sel, nullptr, cloud, b, G, out_idx, out_centers);
 }
 
-template <int PPT, typename IdxT>
-int launch_reg(const float* xyz, int B, int N, int G, const int64_t* start_idx, int skip_small, void* out_idx,
-               float* out_centers, int threads, cudaStream_t st) {
+template <int PPT, typename IdxT, bool PN2>
+int launch_reg(const float* xyz, int B, int N, int G, const int64_t* start_idx, int skip_small, Pn2Order ord,
+               void* out_idx, float* out_centers, int threads, cudaStream_t st) {
   const size_t smem = (size_t)3 * N * sizeof(float) + (size_t)G * sizeof(int);
-  auto kern = fps_reg_kernel<PPT, IdxT>;
+  auto kern = fps_reg_kernel<PPT, IdxT, PN2>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
@@ -289,14 +384,19 @@ int launch_reg(const float* xyz, int B, int N, int G, const int64_t* start_idx, 
       return UA_ERR_CUDA;
     }
   }
-  kern<<<B, threads, smem, st>>>(xyz, N, G, (const long long*)start_idx, skip_small, (IdxT*)out_idx, out_centers);
+  kern<<<B, threads, smem, st>>>(xyz, N, G, (const long long*)start_idx, skip_small, ord, (IdxT*)out_idx, out_centers);
   return check_launch("ua_fps_f32");
 }
 
-template <typename IdxT>
+template <typename IdxT, bool PN2>
 int dispatch(const float* xyz, int B, int N, int G, const int64_t* start_idx, int skip_small, void* out_idx,
              float* out_centers, float* scratch, cudaStream_t st) {
+  Pn2Order ord;
+  ord.lg = 0;
+  while ((2 << ord.lg) <= N && (2 << ord.lg) <= 512) ++ord.lg;     // upstream opt_n_threads(N)
+  ord.q = (N + (1 << ord.lg) - 1) >> ord.lg;
   if (N > UA_FPS_MAX_REG_POINTS) {
+    UA_UNSUPPORTED(PN2, "ua_fps_f32: the pointnet2_ops arithmetic is implemented for N <= %d", UA_FPS_MAX_REG_POINTS);
     UA_REQUIRE(scratch != nullptr, "ua_fps_f32: N=%d > %d needs a [B,N] f32 scratch", N, UA_FPS_MAX_REG_POINTS);
     UA_UNSUPPORTED(G > 40000, "ua_fps_f32: G=%d too large for the large-cloud path", G);
     const size_t smem = (size_t)G * sizeof(int);
@@ -315,7 +415,7 @@ int dispatch(const float* xyz, int B, int N, int G, const int64_t* start_idx, in
       const int threads = (((chunk + kFpsClusterPpt - 1) / kFpsClusterPpt) + 31) / 32 * 32;
       if (threads <= 512) {
         const size_t smem = (size_t)3 * N * sizeof(float) + (size_t)G * sizeof(int);
-        auto kern = fps_cluster_kernel<IdxT>;
+        auto kern = fps_cluster_kernel<IdxT, PN2>;
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(C, B, 1);
@@ -326,7 +426,7 @@ int dispatch(const float* xyz, int B, int N, int G, const int64_t* start_idx, in
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = C, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr, cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, xyz, N, G, chunk, (const long long*)start_idx, skip_small,
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, xyz, N, G, chunk, (const long long*)start_idx, skip_small, ord,
                                            (IdxT*)out_idx, out_centers);
         if (e != cudaSuccess) {
           set_error("ua_fps_f32(cluster): launch failed: %s", cudaGetErrorString(e));
@@ -350,12 +450,12 @@ int dispatch(const float* xyz, int B, int N, int G, const int64_t* start_idx, in
   }
   int threads = (((N + ppt - 1) / ppt) + 31) / 32 * 32;
   switch (ppt) {
-    case 1: return launch_reg<1, IdxT>(xyz, B, N, G, start_idx, skip_small, out_idx, out_centers, threads, st);
-    case 2: return launch_reg<2, IdxT>(xyz, B, N, G, start_idx, skip_small, out_idx, out_centers, threads, st);
-    case 4: return launch_reg<4, IdxT>(xyz, B, N, G, start_idx, skip_small, out_idx, out_centers, threads, st);
-    case 8: return launch_reg<8, IdxT>(xyz, B, N, G, start_idx, skip_small, out_idx, out_centers, threads, st);
-    case 12: return launch_reg<12, IdxT>(xyz, B, N, G, start_idx, skip_small, out_idx, out_centers, threads, st);
-    default: return launch_reg<16, IdxT>(xyz, B, N, G, start_idx, skip_small, out_idx, out_centers, threads, st);
+    case 1: return launch_reg<1, IdxT, PN2>(xyz, B, N, G, start_idx, skip_small, ord, out_idx, out_centers, threads, st);
+    case 2: return launch_reg<2, IdxT, PN2>(xyz, B, N, G, start_idx, skip_small, ord, out_idx, out_centers, threads, st);
+    case 4: return launch_reg<4, IdxT, PN2>(xyz, B, N, G, start_idx, skip_small, ord, out_idx, out_centers, threads, st);
+    case 8: return launch_reg<8, IdxT, PN2>(xyz, B, N, G, start_idx, skip_small, ord, out_idx, out_centers, threads, st);
+    case 12: return launch_reg<12, IdxT, PN2>(xyz, B, N, G, start_idx, skip_small, ord, out_idx, out_centers, threads, st);
+    default: return launch_reg<16, IdxT, PN2>(xyz, B, N, G, start_idx, skip_small, ord, out_idx, out_centers, threads, st);
   }
 }
 
@@ -369,6 +469,9 @@ extern "C" int ua_fps_f32(const float* xyz, int B, int N, int G, const int64_t* 
   UA_REQUIRE(B >= 0 && N >= 1 && G >= 1, "ua_fps_f32: bad sizes B=%d N=%d G=%d", B, N, G);
   if (B == 0) return UA_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  return idx_is_i64 ? dispatch<long long>(xyz, B, N, G, start_idx, skip_small_norm, out_idx, out_centers, scratch, st)
-                    : dispatch<int>(xyz, B, N, G, start_idx, skip_small_norm, out_idx, out_centers, scratch, st);
+  if (skip_small_norm & UA_FPS_POINTNET2)
+    return idx_is_i64 ? dispatch<long long, true>(xyz, B, N, G, start_idx, 0, out_idx, out_centers, scratch, st)
+                      : dispatch<int, true>(xyz, B, N, G, start_idx, 0, out_idx, out_centers, scratch, st);
+  return idx_is_i64 ? dispatch<long long, false>(xyz, B, N, G, start_idx, skip_small_norm & 1, out_idx, out_centers, scratch, st)
+                    : dispatch<int, false>(xyz, B, N, G, start_idx, skip_small_norm & 1, out_idx, out_centers, scratch, st);
 }

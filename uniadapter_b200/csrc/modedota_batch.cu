@@ -266,15 +266,20 @@ __global__ void __launch_bounds__(kBT, 3) modedota_batch_kernel(const StepParams
 
     // ---- phase 4: M-step on this slice: thread = one column d, MM / MG modes ----------------------------------
     const int MG = (kBT / Ds >= 2 && MM % 2 == 0) ? 2 : 1;     // Ds = 128: two mode groups, else one
-    if (tid < MG * Ds) {
-      const int d = tid % Ds, g = tid / Ds;
-      const size_t gbase = (size_t)item * MM * D + d0 + d;
-      if (MG == 2)
+    if (MG == 2) {
+      if (tid < 2 * Ds) {
+        const int d = tid % Ds, g = tid / Ds;
+        const size_t gbase = (size_t)item * MM * D + d0 + d;
         mstep_column<MM, MM / 2>(sx + (size_t)Bp * Ds + d, Ds, B, s_gamma, g * (MM / 2), s_cold, s_sumg, s_rden, smu + d,
                                  svar + d, p.mu + gbase, p.var + gbase, D);
-      else
+      }
+    } else {
+      // slices wider than the CTA (Ds = 384, 512: D = 1152, 3072, 4096) take several columns per thread
+      for (int d = tid; d < Ds; d += kBT) {
+        const size_t gbase = (size_t)item * MM * D + d0 + d;
         mstep_column<MM, MM>(sx + (size_t)Bp * Ds + d, Ds, B, s_gamma, 0, s_cold, s_sumg, s_rden, smu + d, svar + d,
                              p.mu + gbase, p.var + gbase, D);
+      }
     }
   }
   cluster.sync();   // nobody retires while a peer may still read its partials

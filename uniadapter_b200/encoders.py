@@ -167,12 +167,17 @@ class Uni3DEncoder(nn.Module):
         color = pc[:, :, 3:].contiguous()
         return self.forward(xyz, color)
 
-    def forward(self, pts, colors):
+    def front(self, pts, colors):
+        """Tokenizer + group encoder + position embedding: the (B, 1+G, C) sequence entering the transformer blocks
+        (models/point_encoder.py:192-208)."""
         _, center, features = self.group_divider(pts, colors)
         tokens = _linear(self.encoder2trans, self.encoder(features))
         B = tokens.size(0)
         x = torch.cat((self.cls_token.expand(B, -1, -1), tokens), dim=1)
-        x = x + torch.cat((self.cls_pos.expand(B, -1, -1), self.pos_embed(center)), dim=1)
+        return x + torch.cat((self.cls_pos.expand(B, -1, -1), self.pos_embed(center)), dim=1)
+
+    def forward(self, pts, colors):
+        x = self.front(pts, colors)
         for blk in self.blocks:
             x = blk(x)
         return self.trans2embed(self.fc_norm(self.norm(x[:, 0, :])))

@@ -61,7 +61,13 @@ class StreamEngine:
     """
 
     def __init__(self, encoder, vlm3d, text, num_streams, npoints, cfg, mode_M=8, res_learning=True, device='cuda',
-                 use_graph=True, colored=False, seed=42, batch_views=True):
+                 use_graph=True, colored=False, seed=42, batch_views=True, stream_ids=None, external_rng=False):
+        """``stream_ids``: global index of every local stream (default 0..S-1); stream s draws its jitter noise and FPS
+        start indices from the counter-based generator keyed by ``seed + stream_ids[s]`` (csrc/rng.cu), so what a stream
+        sees does not depend on which streams share its GPU or on the world size.
+        ``external_rng``: the step reads start indices and noise from the static buffers ``start_buf`` (2,S) /
+        ``noise_buf`` (S,N,3) instead, which the caller fills with :meth:`set_rng` before every step (parity harness:
+        replays the draws of a CPU run of the reference, also under CUDA-graph replay)."""
         self.dev = torch.device(device)
         self.encoder, self.vlm3d = encoder, vlm3d
         self.S, self.N = num_streams, npoints
@@ -86,12 +92,19 @@ class StreamEngine:
         self.final = torch.zeros(S, K, device=self.dev)
         self.pred = torch.zeros(S, dtype=torch.int32, device=self.dev)
         self.dota_logits = torch.zeros(S, 1, K, device=self.dev)
-        torch.cuda.manual_seed(seed)
-        from .encoders import set_device_rng
-        set_device_rng(encoder, True)
+        # random inputs of a step: static buffers, filled by csrc/rng.cu inside the step or by set_rng() before it
+        self.external_rng = external_rng
+        self.random_start = vlm3d in ('ulip', 'openshape')      # Uni3D samples from point 0 (pointnet2_ops)
+        ids = list(range(S)) if stream_ids is None else [int(i) for i in stream_ids]
+        if len(ids) != S:
+            raise ValueError("stream_ids must name every local stream")
+        self.stream_seeds = torch.tensor([seed + i for i in ids], dtype=torch.int64, device=self.dev)
+        self.rng_step = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self._rng_done = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.noise_buf = torch.zeros(S, N, 3, device=self.dev)
+        self.start_buf = torch.zeros(2, S, dtype=torch.int64, device=self.dev)
         self.step_idx = 0
         self.graph = None
-        self.inject = None      # parity harness: dict(start, start_aug, noise) for the next eager step
         self._host_out = torch.empty(S, K, dtype=torch.float32).pin_memory() if self.dev.type == 'cuda' else None
 
     # ---- pieces of the step ------------------------------------------------------------------------------------
@@ -104,10 +117,26 @@ class StreamEngine:
         return self.encoder(pc, torch.cat((pc, rgb), dim=-1))
 
     def _set_start(self, start):
-        if start is not None:
+        if start is not None and self.random_start:
             for mod in self.encoder.modules():
                 if hasattr(mod, 'next_start_idx'):
                     mod.next_start_idx = start
+
+    def set_rng(self, start, start_aug, noise):
+        """Parity harness (``external_rng=True``): the FPS start indices (S,) of the sample and of its jittered view and
+        the N(0,1) noise (S,N,3) of the next step, copied into the static buffers the (captured) step reads."""
+        if not self.external_rng:
+            raise RuntimeError("set_rng needs StreamEngine(external_rng=True)")
+        self.start_buf[0].copy_(start.reshape(-1), non_blocking=True)
+        self.start_buf[1].copy_(start_aug.reshape(-1), non_blocking=True)
+        self.noise_buf.copy_(noise, non_blocking=True)
+
+    def _draw(self):
+        """One launch: jitter noise and start indices of all S streams from their own counter-based generators."""
+        rc = _lib.lib().ua_stream_rng_f32(_lib.ptr(self.stream_seeds), _lib.ptr(self.rng_step), self.S, self.N * 3,
+                                          _lib.ptr(self.noise_buf), _lib.ptr(self.start_buf), self.N,
+                                          _lib.ptr(self._rng_done), _lib.stream_ptr())
+        _lib.check(rc, "ua_stream_rng_f32")
 
     @torch.no_grad()
     def _adapt(self):
@@ -118,18 +147,17 @@ class StreamEngine:
         clouds (per-cloud results are unchanged: every kernel of the pass is independent across clouds); the two cache
         steps keep the reference's order."""
         S, K = self.S, self.K
-        inj = self.inject or {}
-        noise = inj['noise'] if 'noise' in inj else torch.randn_like(self.pc)
-        pc2 = torch.cat((self.pc, self.pc + 0.05 * noise), dim=0)          # Uni_Adapter.py:420-421
+        if not self.external_rng:
+            self._draw()
+        pc2 = torch.cat((self.pc, self.pc + 0.05 * self.noise_buf), dim=0)          # Uni_Adapter.py:420-421
         if self.batch_views:
-            if inj.get('start') is not None and inj.get('start_aug') is not None:
-                self._set_start(torch.cat((inj['start'], inj['start_aug'])))
+            self._set_start(self.start_buf.view(-1))
             emb = self._encode(pc2, torch.cat((self.rgb, self.rgb), dim=0))
             emb, emb_aug = emb[:S], emb[S:]
         else:
-            self._set_start(inj.get('start'))
+            self._set_start(self.start_buf[0])
             emb = self._encode(pc2[:S])
-            self._set_start(inj.get('start_aug'))
+            self._set_start(self.start_buf[1])
             emb_aug = self._encode(pc2[S:])
         feats, clip_logits, _, prob, _ = zero_shot_head(emb, self.text)
         x_fit = feats.unsqueeze(1)                                     # (S,1,D): batch 1 per stream
@@ -208,12 +236,19 @@ class DotaEngine:
     index comes from the device generator (graph-safe). One stream: the (K,D,D) covariance stack of DOTA is 42 MB per
     stream at cfg 1 and its kernels take one adapter per launch."""
 
-    def __init__(self, encoder, vlm3d, text, npoints, cfg, device='cuda', use_graph=True, seed=42):
+    def __init__(self, encoder, vlm3d, text, npoints, cfg, device='cuda', use_graph=True, seed=42, stream_id=0,
+                 external_rng=False, external_lambda=False):
+        """``external_rng`` / ``external_lambda`` (parity harness): the step reads the FPS start index from
+        ``start_buf`` (filled by :meth:`set_rng`) and, after its own ``update()``, overwrites Lambda with ``lambda_buf``
+        (filled by :meth:`set_lambda` with the reference's Lambda of that step), so that the fp16 discriminant of the
+        next sample is evaluated on the reference's precision matrix -- both as static buffers, so the
+        captured graph is the path under test."""
         from .dota import DOTA
         self.dev = torch.device(device)
         self.encoder, self.vlm3d, self.cfg = encoder, vlm3d, cfg
         self.text = text.to(self.dev).float().contiguous()
         self.K, self.D = self.text.shape
+        self.N = npoints
         self.adapter = DOTA(cfg, self.D, self.K, torch.full((self.D, self.K), 0.001), device=self.dev)   # Uni_Adapter.py:329-330
         self.pc = torch.zeros(1, npoints, 3, device=self.dev)
         self.rgb = torch.ones(1, npoints, 3, device=self.dev)
@@ -221,11 +256,31 @@ class DotaEngine:
         self.pred = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self._host_out = torch.empty(1, self.K, dtype=torch.float32).pin_memory()
         self.use_graph, self.graph, self.step_idx = use_graph, None, 0
-        torch.cuda.manual_seed(seed)
-        from .encoders import set_device_rng
-        set_device_rng(encoder, True)
+        self.external_rng, self.external_lambda = external_rng, external_lambda
+        self.random_start = vlm3d in ('ulip', 'openshape')
+        self.stream_seeds = torch.tensor([seed + int(stream_id)], dtype=torch.int64, device=self.dev)
+        self.rng_step = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self._rng_done = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self._rng_sink = torch.zeros(4, device=self.dev)
+        self.start_buf = torch.zeros(2, 1, dtype=torch.int64, device=self.dev)
+        self.lambda_buf = torch.zeros_like(self.adapter.Lambda) if external_lambda else None
+
+    def set_rng(self, start):
+        self.start_buf[0].copy_(start.reshape(-1), non_blocking=True)
+
+    def set_lambda(self, lam):
+        self.lambda_buf.copy_(lam, non_blocking=True)
 
     def _encode(self, pc):
+        if self.random_start:
+            if not self.external_rng:
+                rc = _lib.lib().ua_stream_rng_f32(_lib.ptr(self.stream_seeds), _lib.ptr(self.rng_step), 1, 4,
+                                                  _lib.ptr(self._rng_sink), _lib.ptr(self.start_buf), self.N,
+                                                  _lib.ptr(self._rng_done), _lib.stream_ptr())
+                _lib.check(rc, "ua_stream_rng_f32")
+            for mod in self.encoder.modules():
+                if hasattr(mod, 'next_start_idx'):
+                    mod.next_start_idx = self.start_buf[0]
         if self.vlm3d == 'uni3d':
             return self.encoder.encode_pc(torch.cat((pc, self.rgb), dim=-1))
         if self.vlm3d == 'ulip':
@@ -239,6 +294,9 @@ class DotaEngine:
         dl = a.predict(feats.mean(0).unsqueeze(0).half())
         a.fit(feats, prob)
         a.update()
+        self.own_lambda = a.Lambda.clone() if self.external_lambda else None    # what update() produced (checked apart)
+        if self.external_lambda:
+            a.Lambda.copy_(self.lambda_buf)
         final, arg, _ = fuse_logits(clip_logits, dl, a.c, cfg['rho'], cfg['eta'], feats.shape[0], 'dota')
         self.final.copy_(final)
         self.pred.copy_(arg)

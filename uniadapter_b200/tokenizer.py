@@ -17,6 +17,7 @@ from torch import nn
 from . import _lib
 
 _FPS_MAX_REG_POINTS = 16384
+UA_FPS_POINTNET2 = 2      # include/ua_b200.h
 
 
 def _f32c(t: torch.Tensor) -> torch.Tensor:
@@ -30,10 +31,12 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
 # ----------------------------------------------------------------------------------------------------------
 def fps_sample(xyz: torch.Tensor, npoint: int, start_idx: torch.Tensor | None = None, *,
                skip_small_norm: bool = False, idx_dtype: torch.dtype = torch.int64,
-               want_idx: bool = True, want_centers: bool = True):
+               want_idx: bool = True, want_centers: bool = True, pointnet2: bool = False):
     """FPS over every cloud of ``xyz`` (B,N,3). Returns (idx (B,G) | None, centers (B,G,3) | None).
 
     ``start_idx`` (B,) int64 gives the first sample of each cloud (None -> 0, the pointnet2_ops convention).
+    ``pointnet2``: the published pointnet2_ops kernel's own arithmetic (FMA-contracted distances, near-origin points
+    never take part, ties resolved like upstream's left-biased reduction tree) instead of the torch FPS arithmetic of misc.py / pointnet_util.py.
     """
     xyz = _f32c(xyz)
     B, N, ch = xyz.shape
@@ -48,7 +51,8 @@ def fps_sample(xyz: torch.Tensor, npoint: int, start_idx: torch.Tensor | None = 
         start_idx = start_idx.to(device=xyz.device, dtype=torch.int64).contiguous()
         if start_idx.numel() != B:
             raise ValueError("start_idx must have one entry per cloud")
-    rc = _lib.lib().ua_fps_f32(_lib.ptr(xyz), B, N, int(npoint), _lib.ptr(start_idx), int(skip_small_norm),
+    rc = _lib.lib().ua_fps_f32(_lib.ptr(xyz), B, N, int(npoint), _lib.ptr(start_idx),
+                               UA_FPS_POINTNET2 if pointnet2 else int(bool(skip_small_norm)),
                                _lib.ptr(idx), int(idx_dtype == torch.int64), _lib.ptr(centers), _lib.ptr(scratch),
                                _lib.stream_ptr())
     _lib.check(rc, "ua_fps_f32")
@@ -113,8 +117,9 @@ def ball_group(xyz: torch.Tensor, centers: torch.Tensor, radius: float, nsample:
 # reference-named entry points
 # ----------------------------------------------------------------------------------------------------------
 def furthest_point_sample(xyz: torch.Tensor, npoint: int) -> torch.Tensor:
-    """pointnet2_utils.furthest_point_sample: (B,N,3) -> (B,npoint) int32, first sample = point 0."""
-    idx, _ = fps_sample(xyz, npoint, None, idx_dtype=torch.int32, want_centers=False)
+    """pointnet2_utils.furthest_point_sample: (B,N,3) -> (B,npoint) int32, first sample = point 0, in the published
+    kernel's arithmetic and tie order (sampling_gpu.cu of pointnet2_ops_lib 3.0.0)."""
+    idx, _ = fps_sample(xyz, npoint, None, idx_dtype=torch.int32, want_centers=False, pointnet2=True)
     return idx
 
 
@@ -132,8 +137,8 @@ def gather_operation(features: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
 
 
 def fps_uni3d(data: torch.Tensor, number: int) -> torch.Tensor:
-    """models/point_encoder.py:7-14 fps(data, number): FPS from point 0, returns the sampled points (B,G,3)."""
-    _, centers = fps_sample(data, number, None, want_idx=False)
+    """models/point_encoder.py:7-14 fps(data, number): pointnet2_ops FPS from point 0, returns the sampled points (B,G,3)."""
+    _, centers = fps_sample(data, number, None, want_idx=False, pointnet2=True)
     return centers
 
 
@@ -191,12 +196,14 @@ class Group(nn.Module):
     ``forward(xyz, color)`` (Uni3D, point_encoder.py:99-127) returns (neighborhood, center, features)."""
 
     def __init__(self, num_group: int, group_size: int, random_start: bool = False, skip_small_norm: bool = False,
-                 device_rng: bool = False):
+                 device_rng: bool = False, pointnet2: bool | None = None):
         super().__init__()
         self.num_group = num_group
         self.group_size = group_size
         self.random_start = random_start      # True: ULIP (torch.randint start); False: Uni3D (pointnet2, start 0)
         self.skip_small_norm = skip_small_norm
+        # Uni3D samples with the pointnet2_ops extension (models/point_encoder.py:12): its own arithmetic and tie order
+        self.pointnet2 = (not random_start) if pointnet2 is None else pointnet2
         # False: draw the start on the global CPU generator exactly like the reference (misc.py:52);
         # True: draw it on the device generator (no host round-trip: required inside CUDA graphs)
         self.device_rng = device_rng
@@ -209,7 +216,8 @@ class Group(nn.Module):
             start, self.next_start_idx = self.next_start_idx, None
         elif self.random_start:
             start = torch.randint(0, N, (B,), dtype=torch.long, device=xyz.device if self.device_rng else 'cpu')
-        _, center = fps_sample(xyz, self.num_group, start, skip_small_norm=self.skip_small_norm, want_idx=False)
+        _, center = fps_sample(xyz, self.num_group, start, skip_small_norm=self.skip_small_norm, want_idx=False,
+                               pointnet2=self.pointnet2 and start is None)
         _, neighborhood, features = knn_group(xyz, center, self.group_size, color)
         if color is None:
             return neighborhood, center
