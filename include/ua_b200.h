@@ -249,17 +249,65 @@ long long ua_dota_update_workspace_bytes(int D);
 int ua_dota_update_f32(const float* overall, int D, float eps, void* workspace, void* out_lambda_h,
                        float* out_lambda_f32, void* stream);
 
+/* One cache pass for a whole batch-1 sample step of the reference loop (Uni_Adapter.py:416-430):
+ *     logits = predict(x.half())  ->  fit(x, prob_map)  ->  fit(x_aug, prob_map)
+ * Each class's (M,D) tile is read from HBM once and written once for all three operations (16*K*M*D bytes per sample
+ * step instead of 32 with ua_modedota_step_f32 called twice); bit-identical to that two-call sequence.
+ *   x_fit [S,D] the normalised sample (predict uses its fp16 rounding, Uni_Adapter.py:416), x_fit2 [S,D] the normalised
+ *   jittered view or NULL (one fit), gamma_class [S,ldg] prob_map read at columns [k_gamma_offset, +K),
+ *   out_logits [S,ldo] written at columns [k_out_offset, +K) or NULL (no predict).
+ * Limits: D % 128 == 0, M <= 16, 16-byte aligned pointers, 4*M*D*4 bytes of tiles must fit in shared memory
+ * (UA_ERR_UNSUPPORTED otherwise: the caller falls back to ua_modedota_step_f32).
+ */
+int ua_modedota_sample_step_f32(const float* x_fit, const float* x_fit2, const float* gamma_class, int ldg,
+                                int k_gamma_offset, float* mu, float* var, float* pi, float* c, float* class_counts,
+                                int S, int K, int M, int D, float eps, float* out_logits, int ldo, int k_out_offset,
+                                void* stream);
+
 /* ------------------------------------------------------------------------------------------
- * Class-sharded cache: all-gather of the per-rank logits through NVLink peer memory, one CTA, inside the
- * step's stream / CUDA graph. Replaces the torch.distributed.all_gather of the sharded step (the reference has no
- * multi-GPU path; this is the exchange step of BASELINE cfg 4).
- *   send [n] f32 of this rank; peer_recv_ptrs: DEVICE array [P] of float* (every rank's symmetric receive buffer,
- *   2*P*n floats each, mapped into this process); peer_flag_ptrs: device array [P] of int* (every rank's P flags,
- *   zero-initialised); seq: device int, the exchange counter (advanced by the kernel; all ranks start from 0);
- *   local_out [P*n]: the gathered block in rank order; err: device int, set non-zero when a peer did not arrive in ~3 s.
+ * Class-sharded sample step (BASELINE cfg 4: the Objaverse-LVIS cache split over P GPUs by class):
+ * the pass above over this rank's classes with both logit exchanges and the fusion in the SAME persistent kernel.
+ * The reference has no multi-GPU path; this is the exchange step the north star names (logit all-gather per step),
+ * done with stores into NVLink-mapped peer memory from the kernel itself instead of a collective call.
+ * Class ranges are contiguous, the first K mod P ranks own one class more. Every rank passes the same sample.
+ *   per rank (struct below, a HOST array of n_ranks entries, copied into the kernel parameters): the normalised sample / jittered view, its zero-shot logits
+ *   clip_local [K_local] (ua_head_f32 on its text rows), its state shard, and
+ *     peer_recv: device array [P] of float* -- every rank's symmetric receive buffer, 2*P*2*K_pad floats
+ *                ([parity][rank][0: zero-shot | 1: cache][K_pad]), mapped into this process;
+ *     peer_flag: device array [P] of int* -- every rank's 2*P flags ([exchange][rank]), zero-initialised;
+ *     seq (device int, step counter, advanced by the kernel; all ranks start from 0), err (device int: 1 = a peer's
+ *     zero-shot logits did not arrive, cache untouched; 2 = a peer's cache logits did not arrive or the peer aborted;
+ *     outputs are NaN / -1 then), done (zeroed u32 scratch), c_sum (device float: sum of the soft counts so far, K at
+ *     start; the kernel adds the fits of the step -- closed form);
+ *     out_final [K], out_argmax [1], out_clip / out_dota [K] or NULL: replicated results of the step.
+ *   n_ranks = 1: this process' rank (ONE struct). n_ranks = P <= 8: single-GPU emulation of all P ranks in one
+ *   cooperative launch (tests); all "peer" buffers then live on the one device.
+ * The launch is cooperative (all CTAs co-resident: they wait for one another through the peers).
  * ---------------------------------------------------------------------------------------- */
-int ua_p2p_allgather_f32(const float* send, int n, const void* peer_recv_ptrs, const void* peer_flag_ptrs, int rank,
-                         int P, int* seq, float* local_out, int* err, void* stream);
+typedef struct ua_shard_rank {
+  const float* x_fit;
+  const float* x_fit2;
+  const float* clip_local;
+  float* mu;
+  float* var;
+  float* pi;
+  float* c;
+  float* class_counts;
+  float* const* peer_recv;
+  int* const* peer_flag;
+  int* seq;
+  int* err;
+  uint32_t* done;
+  float* c_sum;
+  float* out_final;
+  int* out_argmax;
+  float* out_clip;
+  float* out_dota;
+  int rank;
+  int reserved;
+} ua_shard_rank;
+int ua_modedota_sharded_step_f32(const ua_shard_rank* ranks, int n_ranks, int P, int K, int K_pad, int M, int D,
+                                 float eps, float rho, float eta, void* stream);
 
 #ifdef __cplusplus
 }

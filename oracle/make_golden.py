@@ -182,25 +182,15 @@ def alignment_goldens():
 
 def e2e_goldens():
     """The reference's per-sample loop (Uni_Adapter.py:368-579, batch 1) with its own ULIP PointBERT modules,
-    get_logits_wrapper, DOTA / DOTA_mix, compute_text_alignment_loss and Adam, run on the CPU. The loop body is
-    restated here only because test_zeroshot_3d_core hard-codes torch.cuda events; every numerical call is the
-    reference's. Also checks that uniadapter_b200.encoders.UlipPointBert reproduces the reference's random init."""
-    import torch.nn.functional as F
+    get_logits_wrapper, DOTA / DOTA_mix, compute_text_alignment_loss and Adam, run on the CPU through
+    oracle.ref_loop.ReferenceStream (which restates only the loop scaffolding: test_zeroshot_3d_core hard-codes
+    torch.cuda events). Also checks that uniadapter_b200.encoders.UlipPointBert reproduces the reference's random init."""
     from uniadapter_b200.encoders import UlipPointBert
-    _, _, penc = R.ulip_pointbert()
-    ua = R.uni_adapter()
-    dm, dt = R.dota_mixture(), R.dota()
+    from . import ref_loop
     for name in cases.E2E:
         inp = cases.e2e_inputs(name)
         T, N, K, M, depth = inp["T"], inp["N"], inp["K"], inp["M"], inp["depth"]
-        margs = types.SimpleNamespace(pc_feat_dim=768, pc_depth=depth, drop_path_rate=0.0, num_head=6, group_size=32,
-                                      num_group=512, encoder_dim=256)
-        torch.manual_seed(cases.E2E_MODEL_SEED)
-        trunk = penc.PointTransformer(margs)                       # models/ulip/pointbert/point_encoder.py:103
-        proj = torch.empty(768, 512)
-        torch.nn.init.normal_(proj, std=768 ** -0.5)
-        trunk.eval()
-        model = lambda xyz: trunk(xyz) @ proj                      # models/ulip/ulip_model.py:15-18
+        model, trunk, proj = ref_loop.ulip_reference_model(depth, cases.E2E_MODEL_SEED)
         torch.manual_seed(cases.E2E_MODEL_SEED)
         mine = UlipPointBert(depth=depth).eval()
         ref_sd = list(trunk.state_dict().values())
@@ -208,66 +198,20 @@ def e2e_goldens():
         assert len(ref_sd) == len(my_sd) and all(torch.equal(a, b) for a, b in zip(ref_sd, my_sd)), "init mismatch"
         assert torch.equal(mine.pc_projection, proj)
 
-        text = T_(inp["text"])
-        pcs = T_(inp["pc"])
-        args = types.SimpleNamespace(vlm3d='ulip')
-        use_mode = M > 0
-        if use_mode:
-            adapter = dm.DOTA_mix(CFG, 512, K, text.t().contiguous(), num_modes=M)
-        else:
-            adapter = dt.DOTA(CFG, 512, K, torch.full((512, K), 0.001))
-        if inp["res_learning"]:
-            res = torch.zeros_like(text, requires_grad=True)
-            opt = torch.optim.Adam([res], lr=0.001)
+        text, pcs = T_(inp["text"]), T_(inp["pc"])
+        stream = ref_loop.ReferenceStream(model, 'ulip', text, CFG, 512, M, inp["res_learning"])
         torch.manual_seed(cases.E2E_LOOP_SEED)
         finals, clips, dls, lambdas, overall_diag = [], [], [], [], []
-        with torch.no_grad():
-            for i in range(T):
-                pc = pcs[i:i + 1]
-                rgb = torch.ones_like(pc)
-                feature = torch.cat((pc, rgb), dim=-1)
-                if inp["res_learning"]:
-                    clip_weights = F.normalize(text + res.detach(), dim=1).t()
-                else:
-                    clip_weights = text.t()
-                feats, clip_logits, loss, prob_map, pred = ua.get_logits_wrapper(args, model, feature, clip_weights)
-                dl = adapter.predict(feats.mean(0).unsqueeze(0).half())
-                adapter.fit(feats, prob_map)
-                if use_mode:
-                    pc_aug = pc + 0.05 * torch.randn_like(pc)
-                    feats_aug, _, _, _, _ = ua.get_logits_wrapper(args, model, torch.cat((pc_aug, rgb), dim=-1), clip_weights)
-                    feats_aug = feats_aug / feats_aug.norm(dim=-1, keepdim=True)
-                    adapter.fit(feats_aug, prob_map)
-                    adapter.update()
-                    if i > 0 and inp["res_learning"]:
-                        with torch.enable_grad():
-                            emb = text + res
-                            emb = emb / emb.norm(dim=1, keepdim=True)
-                            al, _ = ua.compute_text_alignment_loss(emb, adapter)
-                            for _ in range(10):
-                                opt.zero_grad()
-                                al.backward()
-                                opt.step()
-                                emb = text + res
-                                emb = emb / emb.norm(dim=1, keepdim=True)
-                                al, _ = ua.compute_text_alignment_loss(emb, adapter)
-                    w = torch.clamp(CFG['rho'] * adapter.c.mean() / feats.size(0), max=CFG['eta'])
-                    d = w * dl
-                    ec, ed = ua.softmax_entropy(clip_logits), ua.softmax_entropy(d)
-                    wc, wd = 1 / (ec + 1e-3), 1 / (ed + 1e-3)
-                    wc = wc / (wc + wd)
-                    wd = wd / (wc + wd)
-                    final = wc * clip_logits + wd * d
-                else:
-                    adapter.update()
-                    lambdas.append(adapter.Lambda.clone())                     # fp16 (D,D) after this step's update
-                    overall_diag.append(torch.diagonal(adapter.overall_Sigma).clone())
-                    w = torch.clamp(CFG['rho'] * adapter.c.mean() / feats.size(0), max=CFG['eta'])
-                    final = (clip_logits + w * dl).float()
-                finals.append(final), clips.append(clip_logits), dls.append(dl.float())
-        extra = dict(residual=res.detach()) if inp["res_learning"] else {}
-        if not use_mode:
-            extra.update(Lambda=torch.stack(lambdas), overall_diag=torch.stack(overall_diag), mu=adapter.mu, c=adapter.c)
+        for i in range(T):
+            out = stream.step(pcs[i:i + 1], torch.ones_like(pcs[i:i + 1]))
+            finals.append(out["final"]), clips.append(out["clip_logits"]), dls.append(out["dota_logits"])
+            if M == 0:
+                lambdas.append(stream.adapter.Lambda.clone())                  # fp16 (D,D) after this step's update
+                overall_diag.append(torch.diagonal(stream.adapter.overall_Sigma).clone())
+        extra = dict(residual=stream.res.detach()) if inp["res_learning"] else {}
+        if M == 0:
+            extra.update(Lambda=torch.stack(lambdas), overall_diag=torch.stack(overall_diag), mu=stream.adapter.mu,
+                         c=stream.adapter.c)
         save(name, inp, final_logits=torch.cat(finals), clip_logits=torch.cat(clips), dota_logits=torch.cat(dls),
              pred=torch.cat(finals).argmax(1).to(torch.int32), **extra)
 
@@ -277,15 +221,11 @@ def e2e_openshape_goldens():
     PointPatchTransformer (models/openshape/ppta.py:85-148,181-186 = scaling 4, at reduced depth) with FPS + ball query
     + sample_and_group from models/openshape/pointnet_util.py, coloured clouds of 10 000 points, on the CPU."""
     from uniadapter_b200.encoders import OpenShapePPAT
-    _, ppta = R.openshape_ppta()
-    ua = R.uni_adapter()
-    dm = R.dota_mixture()
+    from . import ref_loop
     for name in cases.E2E_OSHAPE:
         inp = cases.e2e_oshape_inputs(name)
         T, N, S, K, M, depth = inp["T"], inp["N"], inp["S"], inp["K"], inp["M"], inp["depth"]
-        torch.manual_seed(cases.E2E_MODEL_SEED)
-        ref = ppta.Projected('global', ppta.PointPatchTransformer('global', None, 512, depth, 8, 512 * 3, 256, S, 0.2, 64, 6),
-                             torch.nn.Linear(512, 1280)).eval()                    # ppta.py:181-186 at `depth`
+        ref = ref_loop.openshape_reference_model(depth, S, cases.E2E_MODEL_SEED)
         torch.manual_seed(cases.E2E_MODEL_SEED)
         mine = OpenShapePPAT(depth=depth, patches=S).eval()
         ref_sd = [v for k, v in ref.state_dict().items()]
@@ -293,31 +233,13 @@ def e2e_openshape_goldens():
         assert len(ref_sd) == len(my_sd) and all(a.shape == b.shape and torch.equal(a, b) for a, b in zip(ref_sd, my_sd)), \
             "OpenShapePPAT does not reproduce the reference's random init"
         text, pcs, rgbs = T_(inp["text"]), T_(inp["pc"]), T_(inp["rgb"])
-        args = types.SimpleNamespace(vlm3d='openshape')
-        adapter = dm.DOTA_mix(CFG, 1280, K, text.t().contiguous(), num_modes=M)
+        stream = ref_loop.ReferenceStream(ref, 'openshape', text, CFG, 1280, M, False)
         torch.manual_seed(cases.E2E_LOOP_SEED)
         finals, clips, dls = [], [], []
-        with torch.no_grad():
-            for i in range(T):
-                pc, rgb = pcs[i:i + 1], rgbs[i:i + 1]
-                feature = torch.cat((pc, rgb), dim=-1)
-                clip_weights = text.t()
-                feats, clip_logits, loss, prob_map, pred = ua.get_logits_wrapper(args, ref, feature, clip_weights)
-                dl = adapter.predict(feats.mean(0).unsqueeze(0).half())
-                adapter.fit(feats, prob_map)
-                pc_aug = pc + 0.05 * torch.randn_like(pc)
-                feats_aug, _, _, _, _ = ua.get_logits_wrapper(args, ref, torch.cat((pc_aug, rgb), dim=-1), clip_weights)
-                feats_aug = feats_aug / feats_aug.norm(dim=-1, keepdim=True)
-                adapter.fit(feats_aug, prob_map)
-                adapter.update()
-                w = torch.clamp(CFG['rho'] * adapter.c.mean() / feats.size(0), max=CFG['eta'])
-                d = w * dl
-                ec, ed = ua.softmax_entropy(clip_logits), ua.softmax_entropy(d)
-                wc, wd = 1 / (ec + 1e-3), 1 / (ed + 1e-3)
-                wc = wc / (wc + wd)
-                wd = wd / (wc + wd)
-                final = wc * clip_logits + wd * d
-                finals.append(final), clips.append(clip_logits), dls.append(dl.float())
+        for i in range(T):
+            out = stream.step(pcs[i:i + 1], rgbs[i:i + 1])
+            finals.append(out["final"]), clips.append(out["clip_logits"]), dls.append(out["dota_logits"])
+        adapter = stream.adapter
         save(name, inp, final_logits=torch.cat(finals), clip_logits=torch.cat(clips), dota_logits=torch.cat(dls),
              pred=torch.cat(finals).argmax(1).to(torch.int32), c=adapter.c, pi=adapter.pi,
              mu_sample=adapter.mu[:, :, ::8].contiguous())

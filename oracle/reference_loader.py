@@ -11,7 +11,8 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("UA_REFERENCE_ROOT", "/root/reference")
+_LOCAL_COPY = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")      # oracle/fetch_ref.py (git-ignored)
+REF_ROOT = os.environ.get("UA_REFERENCE_ROOT") or ("/root/reference" if os.path.isdir("/root/reference") else _LOCAL_COPY)
 
 
 def available() -> bool:

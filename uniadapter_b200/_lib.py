@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libua_b200.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 UA_OK = 0
+UA_ERR_UNSUPPORTED = -2
 _lib = None
 
 _P = C.c_void_p
@@ -38,6 +39,8 @@ SIGNATURES = {
     "ua_head_prepare_f32": (_I, [_P, _I, _I, _F, _P, _P, _P, _P]),
     "ua_row_stats_f32": (_I, [_P, _I, _I, C.c_longlong, _P, _P, _P, _P]),
     "ua_modedota_step_f32": (_I, [_P, _I, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _I, _I, _P]),
+    "ua_modedota_sample_step_f32": (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _I, _I, _P]),
+    "ua_modedota_sharded_step_f32": (_I, [_P, _I, _I, _I, _I, _I, _I, _F, _F, _F, _P]),
     "ua_fuse_logits_f32": (_I, [_P, _P, _I, _I, _I, _P, _I, _I, _F, _F, _F, _F, _F, _I, _P, _P, _P, _P]),
     "ua_stream_rng_f32": (_I, [_P, _P, _I, C.c_longlong, _P, _P, _I, _P, _P]),
     "ua_residual_scratch_floats": (C.c_longlong, [_I, _I, _I, _I]),
@@ -56,10 +59,17 @@ SIGNATURES = {
     "ua_dota_fit_f32": (_I, [_P, _P, _I, _P, _P, _P, _P, _I, _I, _P]),
     "ua_dota_predict_f16": (_I, [_P, _I, _P, _P, _I, _I, _P, _P]),
     "ua_dota_regularize_f32": (_I, [_P, _I, _F, _P, _P]),
-    "ua_p2p_allgather_f32": (_I, [_P, _I, _P, _P, _I, _I, _P, _P, _P, _P]),
     "ua_dota_update_workspace_bytes": (C.c_longlong, [_I]),
     "ua_dota_update_f32": (_I, [_P, _I, _F, _P, _P, _P, _P]),
 }
+
+
+class ShardRank(C.Structure):
+    """``ua_shard_rank`` of include/ua_b200.h (a host array; the library copies it into the kernel parameters)."""
+    _fields_ = [("x_fit", _P), ("x_fit2", _P), ("clip_local", _P), ("mu", _P), ("var", _P), ("pi", _P), ("c", _P),
+                ("class_counts", _P), ("peer_recv", _P), ("peer_flag", _P), ("seq", _P), ("err", _P), ("done", _P),
+                ("c_sum", _P), ("out_final", _P), ("out_argmax", _P), ("out_clip", _P), ("out_dota", _P), ("rank", _I),
+                ("reserved", _I)]
 
 
 class UaError(RuntimeError):

@@ -5,48 +5,10 @@
 //           (torch type promotion of a 0-dim fp32 tensor times a half tensor).
 //   w = min(rho * mean(c) / batch, eta)
 #include "common.cuh"
+#include "fuse_dev.cuh"
 
 namespace ua {
 namespace {
-
-__device__ __forceinline__ float block_sum(float v, float* s_tmp) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
-  v = warp_sum(v);
-  __syncthreads();
-  if (lane == 0) s_tmp[warp] = v;
-  __syncthreads();
-  float t = 0.f;
-  for (int w = 0; w < W; ++w) t += s_tmp[w];
-  return t;
-}
-
-__device__ __forceinline__ float block_max(float v, float* s_tmp) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
-  v = warp_max(v);
-  __syncthreads();
-  if (lane == 0) s_tmp[warp] = v;
-  __syncthreads();
-  float t = -INFINITY;
-  for (int w = 0; w < W; ++w) t = fmaxf(t, s_tmp[w]);
-  return t;
-}
-
-// -sum softmax(v) * log(softmax(v) + 1e-10) over K entries produced by `get(k)`
-template <typename F>
-__device__ __forceinline__ float softmax_entropy(F get, int K, float* s_tmp) {
-  float mx = -INFINITY;
-  for (int k = threadIdx.x; k < K; k += blockDim.x) mx = fmaxf(mx, get(k));
-  mx = block_max(mx, s_tmp);
-  float se = 0.f;
-  for (int k = threadIdx.x; k < K; k += blockDim.x) se += expf(get(k) - mx);
-  se = block_sum(se, s_tmp);
-  float ent = 0.f;
-  for (int k = threadIdx.x; k < K; k += blockDim.x) {
-    const float p = __fdiv_rn(expf(get(k) - mx), se);
-    ent += p * logf(p + 1e-10f);
-  }
-  return -block_sum(ent, s_tmp);
-}
 
 __global__ void __launch_bounds__(256)
     fuse_kernel(const float* __restrict__ clip, const void* __restrict__ dota, int dota_is_f16, int K,
@@ -54,7 +16,7 @@ __global__ void __launch_bounds__(256)
                 float rho,
                 float eta, float batch, int mode, float* __restrict__ out_final, int* __restrict__ out_argmax,
                 float* __restrict__ out_scaled) {
-  __shared__ float s_tmp[8];
+  __shared__ float s_tmp[32];
   __shared__ float s_best[8];
   __shared__ unsigned s_besti[8];
   const int r = blockIdx.x;
@@ -69,8 +31,7 @@ __global__ void __launch_bounds__(256)
     for (int i = threadIdx.x; i < count_c; i += blockDim.x) part += __ldg(crow_c + i);
     csum = block_sum(part, s_tmp);
   }
-  const float cmean = __fdiv_rn(csum, c_count_total);
-  const float w = fminf(__fdiv_rn(__fmul_rn(cmean, rho), batch), eta);
+  const float w = cache_weight(csum, c_count_total, rho, batch, eta);
 
   auto scaled = [&](int k) -> float {
     if (dota_is_f16) {
@@ -84,10 +45,7 @@ __global__ void __launch_bounds__(256)
   if (mode == 1) {
     const float hc = softmax_entropy([&](int k) { return crow[k]; }, K, s_tmp);
     const float hd = softmax_entropy(scaled, K, s_tmp);
-    const float a = __fdiv_rn(1.f, __fadd_rn(hc, 1e-3f));
-    const float b = __fdiv_rn(1.f, __fadd_rn(hd, 1e-3f));
-    wc = __fdiv_rn(a, __fadd_rn(a, b));
-    wd = __fdiv_rn(b, __fadd_rn(wc, b));  // sic: normalised with the updated clip weight
+    entropy_weights(hc, hd, wc, wd);      // sic: the second weight is normalised with the updated clip weight
   }
   float best = -INFINITY;
   unsigned besti = 0xffffffffu;

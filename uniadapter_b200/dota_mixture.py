@@ -119,6 +119,32 @@ class DOTA_mix(nn.Module):
         """predict(x_pred) on the current state, then fit(x_fit, gamma_class) — one pass over the cache."""
         return self._step(x_pred, x_fit, gamma_class)
 
+    @torch.no_grad()
+    def sample_step(self, x, x_aug, prob_map):
+        """The three cache operations of one batch-1 sample (Uni_Adapter.py:416-430) in ONE pass over the cache:
+        ``predict(x.half())`` on the current state, ``fit(x, prob_map)``, ``fit(x_aug, prob_map)`` (``x_aug`` may be
+        None). x, x_aug (1,D) normalised features, prob_map (1,K). Returns the cache logits (1,K); bit-identical to
+        ``predict_then_fit(x.half(), x, prob_map)`` followed by ``fit(x_aug, prob_map)`` (csrc/modedota_sample.cu)."""
+        K, M, D = self.num_classes, self.num_modes, self.input_shape
+        x = x.to(self.device).float().contiguous()
+        prob_map = prob_map.to(self.device).float().contiguous()
+        if x.shape[0] != 1:
+            raise ValueError("sample_step is the batch-1 step of the reference loop")
+        x_aug = x_aug.to(self.device).float().contiguous() if x_aug is not None else None
+        out = torch.empty((1, K), dtype=torch.float32, device=self.device)
+        rc = _lib.lib().ua_modedota_sample_step_f32(
+            _lib.ptr(x), _lib.ptr(x_aug), _lib.ptr(prob_map), K, 0, _lib.ptr(self.mu), _lib.ptr(self.var),
+            _lib.ptr(self.pi), _lib.ptr(self.c), _lib.ptr(self.class_counts), 1, K, M, D, float(self.epsilon),
+            _lib.ptr(out), K, 0, _lib.stream_ptr())
+        if rc == _lib.UA_ERR_UNSUPPORTED:      # shape outside the register tiling: the same three operations, two passes
+            out = self.predict_then_fit(x.half().float(), x, prob_map)
+            if x_aug is not None:
+                self.fit(x_aug, prob_map)
+            return out
+        _lib.check(rc, "ua_modedota_sample_step_f32")
+        self.t += 2 if x_aug is not None else 1
+        return out
+
     def update(self):
         """No-op (diagonal covariance needs no inversion); kept for API compatibility (dota_mixture.py:269-274)."""
         return None

@@ -52,6 +52,21 @@ class MultiStreamModeDota:
         self.t += B
         return out_logits
 
+    def sample_step(self, x, x_aug, gamma_class, out_logits):
+        """predict(x.half()) + fit(x) + fit(x_aug) of every stream in ONE pass over the stacked cache
+        (csrc/modedota_sample.cu). x, x_aug (S,D); gamma_class (S,K); out_logits (S,K) written in place.
+        Returns False when the shape is outside the kernel's register tiling (the caller then runs the two-pass form)."""
+        S, K, M, D = self.S, self.K, self.M, self.D
+        rc = _lib.lib().ua_modedota_sample_step_f32(
+            _lib.ptr(x), _lib.ptr(x_aug), _lib.ptr(gamma_class), K, 0, _lib.ptr(self.mu), _lib.ptr(self.var),
+            _lib.ptr(self.pi), _lib.ptr(self.c), _lib.ptr(self.class_counts), S, K, M, D, float(self.epsilon),
+            _lib.ptr(out_logits), K, 0, _lib.stream_ptr())
+        if rc == _lib.UA_ERR_UNSUPPORTED:
+            return False
+        _lib.check(rc, "ua_modedota_sample_step_f32")
+        self.t += 2
+        return True
+
 
 class StreamEngine:
     """One adaptation step for S streams per call to :meth:`step`.
@@ -78,6 +93,7 @@ class StreamEngine:
         self.use_graph = use_graph
         self.colored = colored
         self.batch_views = batch_views      # both views of a step through the encoder as one batch of 2S clouds
+        self.fused_cache_pass = True        # predict + fit + fit in one cache pass (False: the two-launch sequence)
         S, N, K, D = self.S, self.N, self.K, self.D
         self.adapter = MultiStreamModeDota(cfg, D, K, self.text0, mode_M, S, self.dev)
         # static buffers
@@ -160,11 +176,14 @@ class StreamEngine:
             self._set_start(self.start_buf[1])
             emb_aug = self._encode(pc2[S:])
         feats, clip_logits, _, prob, _ = zero_shot_head(emb, self.text)
-        x_fit = feats.unsqueeze(1)                                     # (S,1,D): batch 1 per stream
-        x_pred = x_fit.half().float()                                  # Uni_Adapter.py:416 rounds through fp16
-        self.adapter.step(x_pred, x_fit, prob.unsqueeze(1), self.dota_logits)
         feats_aug, _, _, _, _ = zero_shot_head(emb_aug, self.text)
-        self.adapter.step(None, feats_aug.unsqueeze(1), prob.unsqueeze(1))
+        # predict (fp16-rounded sample, Uni_Adapter.py:416) + fit + fit on the jittered view: one pass over the cache
+        if not (self.fused_cache_pass and
+                self.adapter.sample_step(feats, feats_aug, prob, self.dota_logits.view(S, K))):
+            x_fit = feats.unsqueeze(1)                                     # (S,1,D): batch 1 per stream
+            x_pred = x_fit.half().float()
+            self.adapter.step(x_pred, x_fit, prob.unsqueeze(1), self.dota_logits)
+            self.adapter.step(None, feats_aug.unsqueeze(1), prob.unsqueeze(1))
         self._clip_logits = clip_logits
 
     @torch.no_grad()

@@ -171,42 +171,9 @@ class ShardedModeDota:
         self.recv = self.ops.empty(self.world, 2, self.K_pad)
         self._graph = None
 
-    def enable_p2p(self):
-        """Replace the NCCL all-gather of the step by the peer-memory exchange kernel (csrc/p2p.cu): symmetric receive
-        and flag buffers from torch.distributed._symmetric_memory (mapped into every rank's address space), one CTA per
-        rank pushes its logits into every peer's buffer over NVLink and waits for the peers' flags. With it the whole
-        step (local logits -> exchange -> replicated softmax / fusion -> local fits) is ONE CUDA graph."""
-        import torch.distributed._symmetric_memory as symm_mem
-        from . import _lib
-        dev = self.send.device
-        n, P = self.send.numel(), self.world
-        group = self.group if self.group is not None else dist.group.WORLD
-        self._sym_recv = symm_mem.empty(2 * P * n, dtype=torch.float32, device=dev)
-        self._sym_flag = symm_mem.empty(P, dtype=torch.int32, device=dev)
-        self._sym_recv.zero_()
-        self._sym_flag.zero_()
-        h_recv = symm_mem.rendezvous(self._sym_recv, group)
-        h_flag = symm_mem.rendezvous(self._sym_flag, group)
-        self._p2p_recv_ptrs = torch.tensor(list(h_recv.buffer_ptrs), dtype=torch.int64, device=dev)
-        self._p2p_flag_ptrs = torch.tensor(list(h_flag.buffer_ptrs), dtype=torch.int64, device=dev)
-        self._p2p_seq = torch.zeros(1, dtype=torch.int32, device=dev)
-        self._p2p_err = torch.zeros(1, dtype=torch.int32, device=dev)
-        self._p2p_handles = (h_recv, h_flag)
-        torch.cuda.synchronize()
-        dist.barrier(group=self.group)          # every rank has zeroed its flags before anybody signals
-        self._p2p = True
-
     def _all_gather(self):
         if self.gather_fn is not None:
             self.gather_fn(self)
-            return
-        if getattr(self, '_p2p', False):
-            from . import _lib
-            rc = _lib.lib().ua_p2p_allgather_f32(_lib.ptr(self.send), self.send.numel(), _lib.ptr(self._p2p_recv_ptrs),
-                                                 _lib.ptr(self._p2p_flag_ptrs), self.rank, self.world,
-                                                 _lib.ptr(self._p2p_seq), _lib.ptr(self.recv), _lib.ptr(self._p2p_err),
-                                                 _lib.stream_ptr())
-            _lib.check(rc, "ua_p2p_allgather_f32")
             return
         if self.world == 1:
             self.recv[0].copy_(self.send)
@@ -262,8 +229,8 @@ class ShardedModeDota:
         the local fits. No host work between the ~15 launches of a step, which is what bounds the eager step (0.3 ms for
         a 33 us cache pass). Call after at least one eager ``step`` (communicator warm-up). ``pred`` of the result is a
         1-element device tensor; inputs are copied into static buffers, outputs are static buffers overwritten by the
-        next replay. (Capturing the NCCL all-gather INSIDE one graph did not complete in the one 2-GPU attempt of round 1;
-        the planned replacement for the eager collective is a peer-memory exchange kernel.)"""
+        next replay. The product path is :class:`FusedShardedModeDota` (one kernel per step, exchange inside); this class
+        keeps the collective-library form for comparison and for the CPU (gloo) tests of the host logic."""
         if self._graph is None:
             self._g_in = feats_raw.clone().contiguous()
             self._g_aug = feats_aug_raw.clone().contiguous()
@@ -271,26 +238,149 @@ class ShardedModeDota:
             self._g_counts = torch.full((1,), closed_form_count_sum(self.K, self.fits, feats_raw.shape[0]),
                                         dtype=torch.float32, device=feats_raw.device)
             fits_before = self.fits
-            ga = torch.cuda.CUDAGraph()
-            if getattr(self, '_p2p', False):                 # peer-memory exchange: the whole step is one graph
-                with torch.cuda.graph(ga):
-                    self.local_logits(self._g_in)
-                    self._all_gather()
-                    self._g_out = self.finish(self._g_aug, device_counts=self._g_counts)
-                self._graph = (ga, None)
-            else:
-                gb = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(ga):
-                    self.local_logits(self._g_in)
-                with torch.cuda.graph(gb, pool=ga.pool()):   # graph B reads graph A's xnorm: one memory pool
-                    self._g_out = self.finish(self._g_aug, device_counts=self._g_counts)
-                self._graph = (ga, gb)
+            ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ga):
+                self.local_logits(self._g_in)
+            with torch.cuda.graph(gb, pool=ga.pool()):   # graph B reads graph A's xnorm: one memory pool
+                self._g_out = self.finish(self._g_aug, device_counts=self._g_counts)
+            self._graph = (ga, gb)
             self.fits = fits_before       # capture runs no kernel: the counters advance on replay
         self._g_in.copy_(feats_raw)
         self._g_aug.copy_(feats_aug_raw)
         self._graph[0].replay()
-        if self._graph[1] is not None:
-            self._all_gather()                                          # the one exchange of the step (NCCL, eager)
-            self._graph[1].replay()
+        self._all_gather()                                              # the one exchange of the step (NCCL, eager)
+        self._graph[1].replay()
         self.fits += 2
         return self._g_out
+
+
+# ----------------------------------------------------------------------------------------------------------
+# 2b. class-sharded cache, product path: one fused kernel per rank and step (csrc/modedota_sample.cu)
+# ----------------------------------------------------------------------------------------------------------
+class _FusedRank:
+    """Device state of one rank: text / cache shard, static inputs, symmetric receive + flag buffers, counters, outputs."""
+
+    def __init__(self, cfg, text, M, P, rank, dev, recv=None, flag=None):
+        from .engine import MultiStreamModeDota
+        K, D = text.shape
+        self.rank = rank
+        self.k_lo, self.k_hi = class_partition(K, P)[rank]
+        self.Kp, self.K_pad = self.k_hi - self.k_lo, padded_shard(K, P)
+        self.text = text[self.k_lo:self.k_hi].to(dev).float().contiguous()
+        self.cache = MultiStreamModeDota(cfg, D, self.Kp, self.text, M, 1, dev)
+        self.x2 = torch.zeros(2, D, device=dev)                      # raw features: sample, jittered view
+        self.xn = torch.zeros(2, D, device=dev)                      # normalised
+        self.clip2 = torch.zeros(2, self.Kp, device=dev)             # local zero-shot logits of both rows (row 0 is used)
+        self.recv = recv if recv is not None else torch.zeros(2 * P * 2 * self.K_pad, device=dev)
+        self.flag = flag if flag is not None else torch.zeros(2 * P, dtype=torch.int32, device=dev)
+        self.seq = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.err = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.done = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.c_sum = torch.full((1,), float(K), dtype=torch.float32, device=dev)     # initial soft counts sum to K
+        self.out_final = torch.zeros(1, K, device=dev)
+        self.out_argmax = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.out_clip = torch.zeros(1, K, device=dev)
+        self.out_dota = torch.zeros(1, K, device=dev)
+
+    def struct(self, recv_ptrs, flag_ptrs):
+        from ._lib import ShardRank
+        c = self.cache
+        return ShardRank(self.xn[0].data_ptr(), self.xn[1].data_ptr(), self.clip2.data_ptr(), c.mu.data_ptr(), c.var.data_ptr(),
+                         c.pi.data_ptr(), c.c.data_ptr(), c.class_counts.data_ptr(), recv_ptrs.data_ptr(), flag_ptrs.data_ptr(),
+                         self.seq.data_ptr(), self.err.data_ptr(), self.done.data_ptr(), self.c_sum.data_ptr(),
+                         self.out_final.data_ptr(), self.out_argmax.data_ptr(), self.out_clip.data_ptr(),
+                         self.out_dota.data_ptr(), self.rank, 0)
+
+
+class FusedShardedModeDota:
+    """Class-sharded MODE-DOTA sample step (BASELINE cfg 4) as ONE persistent kernel per rank and step:
+    ``ua_head_f32`` (normalise the sample and its jittered view, local zero-shot logits) followed by
+    ``ua_modedota_sharded_step_f32`` -- zero-shot logits pushed to every peer over NVLink, gathered prob_map, predict +
+    fit + fit over the local classes with every cache logit stored straight into the peers, second flag exchange,
+    fusion. No collective call, no host work between launches; ``step`` replays one CUDA graph per sample.
+
+    Real ranks: one process per GPU (``torch.distributed`` initialised, NCCL); the receive and flag buffers come from
+    ``torch.distributed._symmetric_memory`` so that every rank's buffers are mapped into every process.
+    ``emulate_world=P``: all P ranks on ONE device, stepped by one cooperative launch (single-GPU tests);
+    ``emulate_only=r`` then launches rank r alone (its peers never arrive: the time-out path)."""
+
+    def __init__(self, cfg, text, M, device, group=None, emulate_world: int | None = None, use_graph: bool = True,
+                 emulate_only: int | None = None):
+        from . import _lib
+        import ctypes as C
+        self.cfg, self.M = cfg, M
+        self.K, self.D = text.shape
+        self.dev = torch.device(device)
+        self.use_graph, self._graph, self.steps = use_graph, None, 0
+        self.emulated = emulate_world is not None
+        if self.emulated:
+            self.P = int(emulate_world)
+            self.ranks = [_FusedRank(cfg, text, M, self.P, r, self.dev) for r in range(self.P)]
+            recvs, flags = [r.recv for r in self.ranks], [r.flag for r in self.ranks]
+            self._recv_ptrs = torch.tensor([t.data_ptr() for t in recvs], dtype=torch.int64, device=self.dev)
+            self._flag_ptrs = torch.tensor([t.data_ptr() for t in flags], dtype=torch.int64, device=self.dev)
+            if emulate_only is not None:      # tests: launch ONE of the emulated ranks, its peers never arrive
+                self.ranks = [self.ranks[emulate_only]]
+        else:
+            import torch.distributed._symmetric_memory as symm_mem
+            self.rank, self.P = world_info()
+            group = group if group is not None else dist.group.WORLD
+            K_pad = padded_shard(self.K, self.P)
+            recv = symm_mem.empty(2 * self.P * 2 * K_pad, dtype=torch.float32, device=self.dev)
+            flag = symm_mem.empty(2 * self.P, dtype=torch.int32, device=self.dev)
+            recv.zero_()
+            flag.zero_()
+            h_recv, h_flag = symm_mem.rendezvous(recv, group), symm_mem.rendezvous(flag, group)
+            self._handles = (h_recv, h_flag)
+            self._recv_ptrs = torch.tensor(list(h_recv.buffer_ptrs), dtype=torch.int64, device=self.dev)
+            self._flag_ptrs = torch.tensor(list(h_flag.buffer_ptrs), dtype=torch.int64, device=self.dev)
+            self.ranks = [_FusedRank(cfg, text, M, self.P, self.rank, self.dev, recv, flag)]
+            torch.cuda.synchronize()
+            dist.barrier(group=group)      # every rank has zeroed its flags before anybody signals
+        self.K_pad = self.ranks[0].K_pad
+        self._structs = (_lib.ShardRank * len(self.ranks))(*[r.struct(self._recv_ptrs, self._flag_ptrs) for r in self.ranks])
+        self._structs_ptr = C.cast(self._structs, C.c_void_p)
+
+    @property
+    def mine(self) -> _FusedRank:
+        return self.ranks[0]
+
+    def _launch(self):
+        from . import _lib
+        lib = _lib.lib()
+        for r in self.ranks:
+            rc = lib.ua_head_f32(_lib.ptr(r.x2), 2, self.D, _lib.ptr(r.text), 1, r.Kp, 100.0, _lib.ptr(r.xn), _lib.ptr(r.clip2),
+                                 None, None, None, _lib.stream_ptr())
+            _lib.check(rc, "ua_head_f32")
+        rc = lib.ua_modedota_sharded_step_f32(self._structs_ptr, len(self.ranks), self.P, self.K, self.K_pad, self.M, self.D,
+                                              float(self.cfg.get('epsilon', 0.001)), float(self.cfg['rho']),
+                                              float(self.cfg['eta']), _lib.stream_ptr())
+        _lib.check(rc, "ua_modedota_sharded_step_f32")
+
+    @torch.no_grad()
+    def step(self, feats_raw: torch.Tensor, feats_aug_raw: torch.Tensor) -> ShardedStepOutput:
+        """feats_raw / feats_aug_raw (1,D): raw encoder outputs of the sample and of its jittered view (the same on every
+        rank). Returns the replicated result of this rank (static buffers, overwritten by the next step)."""
+        for r in self.ranks:
+            r.x2[0].copy_(feats_raw.reshape(-1), non_blocking=True)
+            r.x2[1].copy_(feats_aug_raw.reshape(-1), non_blocking=True)
+        if self.use_graph and self.steps >= 1:
+            if self._graph is None:
+                self._graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._graph):
+                    self._launch()
+            self._graph.replay()
+        else:
+            self._launch()
+        self.steps += 1
+        m = self.mine
+        return ShardedStepOutput(m.out_final, m.out_argmax, m.out_clip, m.out_dota)
+
+    def check(self):
+        """Raise if any in-kernel wait for a peer ran out (host synchronisation: call every N steps and at stream end).
+        After an error the outputs of that step are NaN / -1 and the cache shard of the waiting rank is untouched."""
+        errs = [int(r.err.item()) for r in self.ranks]
+        if any(errs):
+            what = {1: "a peer's zero-shot logits did not arrive", 2: "a peer's cache logits did not arrive (or the peer aborted)"}
+            raise RuntimeError("class-sharded step: " + "; ".join(f"rank {r.rank}: {what.get(e, e)}"
+                                                                   for r, e in zip(self.ranks, errs) if e))
