@@ -60,6 +60,9 @@ def parse_args(argv=None):
     p.add_argument('--num-classes', type=int, default=40, help='classes of the synthetic stream / text features')
     p.add_argument('--stream-length', type=int, default=64, help='samples per synthetic corruption stream')
     p.add_argument('--small-encoder', action='store_true', help='2 transformer blocks (smoke runs)')
+    p.add_argument('--shard-classes', action='store_true',
+                   help='large-vocabulary caches (BASELINE cfg 4): shard the MODE-DOTA cache by class over the ranks of the '
+                        'torchrun job; every rank walks every stream, the logit exchange runs inside the cache kernel')
     p.add_argument('--lockstep', action=argparse.BooleanOptionalAction, default=None,
                    help='advance the corruption streams of this rank together, one CUDA-graph step per sample index '
                         '(default: on for --use-mode-dota at batch size 1); --no-lockstep walks them one after the '
@@ -111,11 +114,32 @@ def main(argv=None):
     args.keep_logits = False
 
     corruptions = CORRUPTIONS if args.corruption == 'all' else [args.corruption]
+    if args.shard_classes:
+        # class-sharded cache: the ranks cooperate on every stream instead of splitting the streams among themselves
+        from uniadapter_b200.adapter import test_zeroshot_3d_sharded
+        summary = {}
+        for s, corr in enumerate(corruptions):
+            dataset = NpyCorruptionStream(args.myroot, corr, args.severity, npoints=args.npoints, dataset=args.dataset_name) if args.myroot else \
+                SyntheticStream(args.stream_length, args.npoints, args.num_classes, seed=args.seed, stream=s,
+                                colored=(args.vlm3d == 'openshape'))
+            args.stream_ids = [s]
+            result = test_zeroshot_3d_sharded(dataset, model, args, name=corr)
+            summary[s] = result
+            if rank == 0:
+                print(f"[{world} rank(s), cache sharded by class] {corr}: acc1 {result['acc1']:.2f} acc3 {result['acc3']:.2f} "
+                      f"acc5 {result['acc5']:.2f} (median {result['median_ms_per_sample']:.3f} ms/sample)", flush=True)
+        if rank == 0:
+            table = {corruptions[s]: summary[s]['acc1'] for s in sorted(summary)}
+            logging.info(f"Summary of Results: {table}")
+            logging.info(f"Average Top-1: {np.mean(list(table.values())):.3f}")
+        if world > 1:
+            dist.destroy_process_group()
+        return summary
     mine = parallel.assign_streams(len(corruptions), world, rank)
     local_results = {}
     if args.lockstep and mine:
         from uniadapter_b200.adapter import test_zeroshot_3d_lockstep
-        datasets = [NpyCorruptionStream(args.myroot, corruptions[s], args.severity, npoints=args.npoints) if args.myroot else
+        datasets = [NpyCorruptionStream(args.myroot, corruptions[s], args.severity, npoints=args.npoints, dataset=args.dataset_name) if args.myroot else
                     SyntheticStream(args.stream_length, args.npoints, args.num_classes, seed=args.seed, stream=s,
                                     colored=(args.vlm3d == 'openshape'))
                     for s in mine]
@@ -140,7 +164,7 @@ def main(argv=None):
         args.corruption = corr
         logging.info(f"\n{'=' * 20} Processing Corruption: {corr} {'=' * 20}")
         if args.myroot:      # the reference's corruption files (data/tta_datasets.py:11-36), memory-mapped
-            dataset = NpyCorruptionStream(args.myroot, corr, args.severity, npoints=args.npoints)
+            dataset = NpyCorruptionStream(args.myroot, corr, args.severity, npoints=args.npoints, dataset=args.dataset_name)
         else:
             dataset = SyntheticStream(args.stream_length, args.npoints, args.num_classes, seed=args.seed, stream=s,
                                       colored=(args.vlm3d == 'openshape'))

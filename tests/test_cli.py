@@ -69,3 +69,32 @@ def test_cli_all_corruptions_in_lockstep(cuda_device, tmp_path):
     import torch
     rows = torch.stack([r['preds'] for r in out.values()])
     assert (rows != rows[0]).any()
+
+
+@pytest.mark.gpu
+def test_cli_class_sharded_cache(cuda_device, tmp_path):
+    """--shard-classes (BASELINE cfg 4): the Uni3D loop with the MODE-DOTA cache behind the fused class-sharded step. One
+    process = one rank (P = 1, the same kernel with an empty exchange); the 4-rank emulation on the same device must give
+    the same predictions and logits (the partition changes no arithmetic)."""
+    import torch
+    m = load_main()
+    base = ['--vlm3d', 'uni3d', '--small-encoder', '--corruption', 'shear', '--stream-length', '6', '--npoints', '1024',
+            '--num-classes', '203', '--mode-M', '8', '--no-res-learning', '--shard-classes', '--output-dir', str(tmp_path)]
+    (res,) = m.main(base).values()
+    assert len(res['times_ms']) == 6 and int(res['preds'].max()) < 203 and res['engine'].graph is not None
+    one = res['engine'].final.clone()
+    import uniadapter_b200.adapter as A
+    orig = A.test_zeroshot_3d_sharded
+
+    def emulated(dataset, model, args, name=None):
+        args.emulate_world = 4
+        return orig(dataset, model, args, name)
+
+    A.test_zeroshot_3d_sharded = emulated
+    try:
+        (res4,) = m.main(base).values()
+    finally:
+        A.test_zeroshot_3d_sharded = orig
+    assert torch.equal(res4['preds'], res['preds'])
+    assert torch.equal(res4['engine'].final, one)
+    assert len(res4['engine'].sharded.ranks) == 4

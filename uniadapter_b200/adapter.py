@@ -227,3 +227,44 @@ def test_zeroshot_3d_lockstep(datasets, model, args, names=None, rng_feed=None, 
                     'name': names[s] if names else str(s),
                     'logits': torch.stack([l[s] for l in all_logits]) if all_logits else None, 'engine': engine})
     return out
+
+
+def test_zeroshot_3d_sharded(dataset, model, args, name=None):
+    """One corruption stream adapted with the MODE-DOTA cache sharded by class over the ranks of the process group
+    (BASELINE cfg 4: large-vocabulary caches; ``main_test-time.py --shard-classes`` under torchrun). Every rank walks the
+    SAME stream (replicated encoder); per sample one CUDA-graph replay of ``engine.ShardedSampleEngine``. Returns the
+    stream's result dict (identical on every rank); raises if a peer ever failed to arrive inside the kernel."""
+    from .engine import ShardedSampleEngine
+    from .streams import PinnedPrefetcher
+    device = torch.device(args.device)
+    cfg = {'epsilon': args.dota_epsilon, 'sigma': args.dota_sigma, 'eta': args.dota_eta, 'rho': args.dota_rho}
+    text = load_text_features(args, device)
+    if not args.use_mode_dota or args.res_learning:
+        raise NotImplementedError("--shard-classes is the MODE-DOTA branch without residual learning (BASELINE cfg 4: the "
+                                  "reference's (K,K,M,D) alignment loss does not exist at K = 1156, SURVEY H8)")
+    engine = ShardedSampleEngine(model, args.vlm3d, text, args.npoints, cfg, mode_M=args.mode_M, device=device,
+                                 use_graph=True, seed=args.seed, stream_id=getattr(args, 'stream_ids', [0])[0],
+                                 emulate_world=getattr(args, 'emulate_world', None))
+    colored = args.vlm3d == 'openshape'
+    feed = PinnedPrefetcher([dataset], args.npoints, with_rgb=colored)
+    hits, preds, times, n = torch.zeros(3), [], [], 0
+    start_event, end_event = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for item in feed:
+        torch.cuda.synchronize()
+        start_event.record()
+        final, _ = engine.step(item[0], item[2]) if colored else engine.step(item[0])
+        end_event.record()
+        torch.cuda.synchronize()
+        times.append(start_event.elapsed_time(end_event))
+        top = final.topk(min(5, final.shape[1]), dim=1).indices[0]
+        match = top.eq(item[1].view(-1)[0])
+        hits += torch.tensor([float(match[:1].any()), float(match[:3].any()), float(match[:5].any())])
+        preds.append(int(top[0]))
+        n += 1
+        if n % 64 == 0:
+            engine.check()
+    engine.check()
+    acc = (100.0 * hits / max(n, 1)).tolist()
+    return {'acc1': acc[0], 'acc3': acc[1], 'acc5': acc[2], 'preds': torch.tensor(preds), 'times_ms': times,
+            'ms_per_sample': sum(times) / max(n, 1), 'median_ms_per_sample': sorted(times)[len(times) // 2] if times else float('nan'),
+            'name': name or '0', 'engine': engine}

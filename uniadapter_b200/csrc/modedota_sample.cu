@@ -35,6 +35,8 @@
 namespace ua {
 
 int g_p2p_timeout_ms = 2000;   // tuning: bound of every in-kernel wait for a peer
+int g_sample_v = 0;            // tuning override: float4s per lane (0 = heuristic)
+int g_sample_g = 0;            // tuning override: warp groups per CTA (0 = heuristic)
 
 namespace {
 
@@ -186,6 +188,11 @@ __global__ void __launch_bounds__(s_max_threads(V, G), 1)
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_part + G * 3 * 32 * 4);  // [NS]
   int* s_issued = reinterpret_cast<int*>(s_bar + 8);                       // [NS] highest class index armed per stage
   float* s_clip = reinterpret_cast<float*>(s_issued + 8);                  // [K] gathered zero-shot row (sharded)
+  // [D] the fp16-rounded sample predict() sees (Uni_Adapter.py:416), rounded once per CTA when there is one stream
+  // [3][D] rows of the sample when there is one stream: its fp16 rounding (what predict() sees, Uni_Adapter.py:416), the
+  // sample, the jittered view -- staged once per CTA, read by every class (shared-memory loads instead of global ones)
+  float* s_rows = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s_clip + (sharded ? lp.Ktot : 0)) + 15) & ~uintptr_t(15));
+  const bool rows_smem = lp.S == 1;
 
   const int total = lp.S * p.K;
   const int first = blockIdx.x, stride = gridDim.x;
@@ -207,6 +214,14 @@ __global__ void __launch_bounds__(s_max_threads(V, G), 1)
     }
     fence_mbar_init();
     for (int j = 0; j < NS && j < n_mine; ++j) issue_load(j);   // the first tiles fly while the exchange below runs
+  }
+  if (rows_smem) {
+    for (int d = tid; d < D; d += T) {
+      const float xv = __ldg(p.x_fit + d);
+      s_rows[d] = __half2float(__float2half_rn(xv));
+      s_rows[D + d] = xv;
+      s_rows[2 * D + d] = fit2 ? __ldg(p.x_fit2 + d) : 0.f;
+    }
   }
   __syncthreads();
 
@@ -262,6 +277,7 @@ __global__ void __launch_bounds__(s_max_threads(V, G), 1)
       if (warp == 0) nx_cc = __ldg(p.class_counts + item);
     };
     if (grp < n_mine) fetch_small(grp);
+    const int nfit = fit2 ? 2 : 1;
 
     int it = 0;   // group-local iteration (parity of the partial-sum buffer)
     for (int j = grp; j < n_mine; j += G, ++it) {
@@ -271,212 +287,162 @@ __global__ void __launch_bounds__(s_max_threads(V, G), 1)
       const int s = item / p.K, k = item - s * p.K;
       const float* t_mu = s_tiles + (size_t)stage * 2 * MD + (size_t)wm * D + d0;
       const float* t_var = t_mu + MD;
-      const float cur_pi = nx_pi, cur_c = nx_c, cur_g = nx_g, cur_cc = nx_cc;
+      const float cur_g = nx_g;
+      float c_cur = nx_c, pi_cur = nx_pi, cc_cur = nx_cc;      // soft counts / mixing weights / class count so far
       if (j + G < n_mine) fetch_small(j + G);
-      const float* xf_row = p.x_fit + (size_t)s * D + d0;     // the sample (L1-resident)
+      // rows of this class's stream: staged in shared memory when there is one stream, else L1-resident global rows
+      const float* row_pred = rows_smem ? s_rows + d0 : nullptr;
+      const float* row_fit0 = rows_smem ? s_rows + D + d0 : p.x_fit + (size_t)s * D + d0;
+      const float* row_fit1 = rows_smem ? s_rows + 2 * D + d0 : (fit2 ? p.x_fit2 + (size_t)s * D + d0 : row_fit0);
 
       // The ring is shared by the groups and an mbarrier parity only tells adjacent phases apart: a group may look at a
       // stage only once the load of ITS class has been armed (by the group that drained the stage's previous class).
-      while (ld_volatile_shared(&s_issued[stage]) < j) {
+      if (lane == 0) {
+        while (ld_volatile_shared(&s_issued[stage]) < j) {
+        }
       }
+      __syncwarp();
       mbar_wait(&s_bar[stage], parity);
 
+      float* o_mu = p.mu + (size_t)item * MD + (size_t)wm * D + d0;
+      float* o_var = p.var + (size_t)item * MD + (size_t)wm * D + d0;
       float4 mu4[V], var4[V];
 #pragma unroll
       for (int v = 0; v < V; ++v) {
         mu4[v] = *reinterpret_cast<const float4*>(t_mu + 128 * v);
         var4[v] = *reinterpret_cast<const float4*>(t_var + 128 * v);
       }
-      // ---- pass 1: log-determinant and Mahalanobis partial sums of predict (fp16-rounded sample) and fit #1 -------
-      float accp = 0.f, accf = 0.f, mprod = 1.f;
-      int esum = 0;
-#pragma unroll
-      for (int v = 0; v < V; ++v) {
-        const float mm[4] = {mu4[v].x, mu4[v].y, mu4[v].z, mu4[v].w};
-        const float vv[4] = {var4[v].x, var4[v].y, var4[v].z, var4[v].w};
-        const float4 t = __ldg(reinterpret_cast<const float4*>(xf_row + 128 * v));
-        const float ff[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float vq = fmaxf(__fadd_rn(vv[q], lp.eps), 1e-8f);
-          const float inv = rcp_rn_normal(vq);   // one correctly-rounded reciprocal shared by both rows
-          if (pred) {
-            const float dq = __fsub_rn(__half2float(__float2half_rn(ff[q])), mm[q]);
-            accp = fmaf(dq * dq, inv, accp);
-          }
-          const float dq = __fsub_rn(ff[q], mm[q]);
-          accf = fmaf(dq * dq, inv, accf);
-          // log-determinant in product form: sum_d log v = ln2 * sum_d e_d + log prod_d m_d, v = m * 2^e, m in [1,2)
-          const uint32_t bits = __float_as_uint(vq);
-          esum += (int)(bits >> 23);
-          mprod *= __uint_as_float((bits & 0x007fffffu) | 0x3f800000u);
-        }
-      }
-      float ld = fmaf((float)(esum - 127 * 4 * V), 0.693147182f, logf(mprod));
-      if (pred) accp = warp_sum(accp);
-      accf = warp_sum(accf);
-      ld = warp_sum(ld);
-      const float logpi = logf(__fadd_rn(cur_pi, 1e-10f));   // off the critical path: before the barrier
-      float* part = s_part + ((grp * 3 + (it & 1)) * 32) * 4;
-      if (lane == 0) *reinterpret_cast<float4*>(part + warp * 4) = make_float4(accp, accf, ld, 0.f);
-      if (G == 1) __syncthreads(); else group_barrier(1 + grp, gwarps * 32);
-      // every warp of the group has pulled the stage into registers: re-arm it NS classes ahead
-      if (warp == 0 && lane == 0 && j + NS < n_mine) {
-        issue_load(j + NS);
-        st_volatile_shared(&s_issued[stage], j + NS);
-      }
-
-      // ---- responsibilities: every warp evaluates all M modes (lane = mode; lanes 8.. idle when M <= 8) ------------
-      float mp = 0.f, mf = 0.f, ldet = 0.f;
-      if (lane < M) {
-        for (int ch = 0; ch < chunks; ++ch) {
-          const float4 q = *reinterpret_cast<const float4*>(part + (lane * chunks + ch) * 4);
-          mp += q.x, mf += q.y, ldet += q.z;
-        }
-      }
-      if (pred) {
-        const float lj = lane < M ? __fadd_rn(logpi, __fmul_rn(-0.5f, __fadd_rn(ldet, mp))) : -INFINITY;
-        const float mx = SHORTM ? modes_max<true>(lj) : modes_max<false>(lj);
-        const float ex = lane < M ? expf(__fsub_rn(lj, mx)) : 0.f;
-        const float se = SHORTM ? modes_sum<true>(ex) : modes_sum<false>(ex);
-        if (warp == 0 && lane == 0) {
-          const float lse = __fadd_rn(logf(se), mx);
-          if (p.out_logits) p.out_logits[(size_t)s * p.ldo + p.ko_off + k] = lse;
-          if (sharded) {   // the predict epilogue writes the class's cache logit straight into every peer
-            const size_t off = ((size_t)(par * sh.P + R.rank) * 2 + 1) * sh.K_pad + k;
-            for (int r = 0; r < sh.P; ++r) R.peer_recv[r][off] = lse;
-          }
-        }
-      }
-      float c_out, pi_out, rd, g0, cold;
-      {
-        const float lj = lane < M ? __fadd_rn(logpi, __fmul_rn(-0.5f, __fadd_rn(ldet, mf))) : -INFINITY;
-        const float mx = SHORTM ? modes_max<true>(lj) : modes_max<false>(lj);
-        const float ex = lane < M ? expf(__fsub_rn(lj, mx)) : 0.f;
-        const float se = SHORTM ? modes_sum<true>(ex) : modes_sum<false>(ex);
-        const float lse = __fadd_rn(logf(se), mx);
-        // gamma[b=0, mode] = gamma_class * exp(log_joint - logsumexp), the reference's form (dota_mixture.py:182-186)
-        const float gam = lane < M ? __fmul_rn(cur_g, expf(__fsub_rn(lj, lse))) : 0.f;
-        const float cnew = __fadd_rn(cur_c, gam);
-        const float rden = rcp_rn_normal(__fadd_rn(cnew, 1e-10f));
-        const float cm = lane < M ? cnew : 0.f;
-        const float ck = SHORTM ? modes_sum<true>(cm) : modes_sum<false>(cm);
-        c_out = cnew;
-        pi_out = __fdiv_rn(cnew, __fadd_rn(ck, 1e-10f));
-        cold = __shfl_sync(kFullMask, cur_c, wm);
-        g0 = __shfl_sync(kFullMask, gam, wm);
-        rd = __shfl_sync(kFullMask, rden, wm);
-      }
-      // ---- M-step #1 on the registers of this warp's (mode, chunk) ---------------------------------------------------
-#pragma unroll
-      for (int v = 0; v < V; ++v) {
-        float mm[4] = {mu4[v].x, mu4[v].y, mu4[v].z, mu4[v].w};
-        float vv[4] = {var4[v].x, var4[v].y, var4[v].z, var4[v].w};
-        const float4 t = __ldg(reinterpret_cast<const float4*>(xf_row + 128 * v));
-        const float ff[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float wx = __fmul_rn(g0, ff[q]);
-          const float wxsq = __fmul_rn(g0, __fmul_rn(ff[q], ff[q]));
-          const float mu_ = mm[q];
-          mm[q] = __fmul_rn(__fadd_rn(__fmul_rn(cold, mu_), wx), rd);
-          const float term2 = __fmul_rn(__fmul_rn(-2.0f, mu_), wx);
-          const float term3 = __fmul_rn(g0, __fmul_rn(mu_, mu_));
-          const float wsd = __fadd_rn(__fadd_rn(wxsq, term2), term3);
-          vv[q] = fmaxf(__fmul_rn(__fadd_rn(__fmul_rn(cold, vv[q]), wsd), rd), 1e-8f);
-        }
-        mu4[v] = make_float4(mm[0], mm[1], mm[2], mm[3]);
-        var4[v] = make_float4(vv[0], vv[1], vv[2], vv[3]);
-      }
-      float cc_out = cur_cc + cur_g;
-      if (fit2) {
-        // ---- pass 2: fit #2 (the jittered view) on the state fit #1 left in the registers ---------------------------
-        const float* x2_row = p.x_fit2 + (size_t)s * D + d0;
-        float acc2 = 0.f, mprod2 = 1.f;
-        int esum2 = 0;
+      // One body for both fits (fit #2 = the same code on the registers fit #1 left): the loop is NOT unrolled, so the
+      // instruction footprint stays inside the instruction cache (the two-copy version spent 21 % of its warp stalls
+      // waiting for instructions: profiles/r2_ncu_sample_step.txt).
+#pragma unroll 1
+      for (int f = 0; f < nfit; ++f) {
+        const float* xrow = f == 0 ? row_fit0 : row_fit1;
+        const bool do_pred = pred && f == 0;
+        // ---- likelihood pass: log-determinant and Mahalanobis partial sums (fit row; predict row on the first pass) ---
+        float accp = 0.f, accf = 0.f, mprod = 1.f;
+        int esum = 0;
 #pragma unroll
         for (int v = 0; v < V; ++v) {
           const float mm[4] = {mu4[v].x, mu4[v].y, mu4[v].z, mu4[v].w};
           const float vv[4] = {var4[v].x, var4[v].y, var4[v].z, var4[v].w};
-          const float4 t = __ldg(reinterpret_cast<const float4*>(x2_row + 128 * v));
+          const float4 t = rows_smem ? *reinterpret_cast<const float4*>(xrow + 128 * v)
+                                     : __ldg(reinterpret_cast<const float4*>(xrow + 128 * v));
           const float ff[4] = {t.x, t.y, t.z, t.w};
+          float pp[4] = {0.f, 0.f, 0.f, 0.f};
+          if (do_pred) {
+            if (rows_smem) {
+              const float4 u = *reinterpret_cast<const float4*>(row_pred + 128 * v);
+              pp[0] = u.x, pp[1] = u.y, pp[2] = u.z, pp[3] = u.w;
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) pp[q] = __half2float(__float2half_rn(ff[q]));   // Uni_Adapter.py:416
+            }
+          }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float vq = fmaxf(__fadd_rn(vv[q], lp.eps), 1e-8f);
-            const float inv = rcp_rn_normal(vq);
+            const float inv = rcp_rn_normal(vq);   // one correctly-rounded reciprocal shared by both rows
+            const float dp = __fsub_rn(pp[q], mm[q]);
+            accp = fmaf(dp * dp, inv, accp);       // (unused on the second pass: three instructions, no branch)
             const float dq = __fsub_rn(ff[q], mm[q]);
-            acc2 = fmaf(dq * dq, inv, acc2);
+            accf = fmaf(dq * dq, inv, accf);
+            // log-determinant in product form: sum_d log v = ln2 * sum_d e_d + log prod_d m_d, v = m * 2^e, m in [1,2)
             const uint32_t bits = __float_as_uint(vq);
-            esum2 += (int)(bits >> 23);
-            mprod2 *= __uint_as_float((bits & 0x007fffffu) | 0x3f800000u);
+            esum += (int)(bits >> 23);
+            mprod *= __uint_as_float((bits & 0x007fffffu) | 0x3f800000u);
           }
         }
-        float ld2 = fmaf((float)(esum2 - 127 * 4 * V), 0.693147182f, logf(mprod2));
-        acc2 = warp_sum(acc2);
-        ld2 = warp_sum(ld2);
-        const float logpi2 = logf(__fadd_rn(pi_out, 1e-10f));
-        float* part2 = s_part + ((grp * 3 + 2) * 32) * 4;
-        if (lane == 0) *reinterpret_cast<float4*>(part2 + warp * 4) = make_float4(0.f, acc2, ld2, 0.f);
+        float ld = fmaf((float)(esum - 127 * 4 * V), 0.693147182f, logf(mprod));
+        accp = warp_sum(accp);
+        accf = warp_sum(accf);
+        ld = warp_sum(ld);
+        const float logpi = logf(__fadd_rn(pi_cur, 1e-10f));   // off the critical path: before the barrier
+        float* part = s_part + ((grp * 3 + (f == 0 ? (it & 1) : 2)) * 32) * 4;
+        if (lane == 0) *reinterpret_cast<float4*>(part + warp * 4) = make_float4(accp, accf, ld, 0.f);
         if (G == 1) __syncthreads(); else group_barrier(1 + grp, gwarps * 32);
-        float mf2 = 0.f, ldet2 = 0.f;
+        // every warp of the group has pulled the stage into registers: re-arm it NS classes ahead
+        if (f == 0 && warp == 0 && lane == 0 && j + NS < n_mine) {
+          issue_load(j + NS);
+          st_volatile_shared(&s_issued[stage], j + NS);
+        }
+
+        // ---- responsibilities: every warp evaluates all M modes (lane = mode; lanes 8.. idle when M <= 8) ----------
+        float mp = 0.f, mf = 0.f, ldet = 0.f;
         if (lane < M) {
           for (int ch = 0; ch < chunks; ++ch) {
-            const float4 q = *reinterpret_cast<const float4*>(part2 + (lane * chunks + ch) * 4);
-            mf2 += q.y, ldet2 += q.z;
+            const float4 q = *reinterpret_cast<const float4*>(part + (lane * chunks + ch) * 4);
+            mp += q.x, mf += q.y, ldet += q.z;
           }
         }
-        const float lj = lane < M ? __fadd_rn(logpi2, __fmul_rn(-0.5f, __fadd_rn(ldet2, mf2))) : -INFINITY;
-        const float mx = SHORTM ? modes_max<true>(lj) : modes_max<false>(lj);
-        const float ex = lane < M ? expf(__fsub_rn(lj, mx)) : 0.f;
-        const float se = SHORTM ? modes_sum<true>(ex) : modes_sum<false>(ex);
-        const float lse = __fadd_rn(logf(se), mx);
-        const float gam = lane < M ? __fmul_rn(cur_g, expf(__fsub_rn(lj, lse))) : 0.f;   // the ORIGINAL prob_map (:430)
-        const float cprev = c_out;
-        const float cnew = __fadd_rn(cprev, gam);
-        const float rden = rcp_rn_normal(__fadd_rn(cnew, 1e-10f));
-        const float cm = lane < M ? cnew : 0.f;
-        const float ck = SHORTM ? modes_sum<true>(cm) : modes_sum<false>(cm);
-        c_out = cnew;
-        pi_out = __fdiv_rn(cnew, __fadd_rn(ck, 1e-10f));
-        const float cold2 = __shfl_sync(kFullMask, cprev, wm);
-        const float g2 = __shfl_sync(kFullMask, gam, wm);
-        const float rd2 = __shfl_sync(kFullMask, rden, wm);
-        cc_out = cc_out + cur_g;
+        {   // (warp collectives stay outside of run-time conditions: the compiler then keeps them in line)
+          const float lj = lane < M ? __fadd_rn(logpi, __fmul_rn(-0.5f, __fadd_rn(ldet, mp))) : -INFINITY;
+          const float mx = SHORTM ? modes_max<true>(lj) : modes_max<false>(lj);
+          const float ex = lane < M ? expf(__fsub_rn(lj, mx)) : 0.f;
+          const float se = SHORTM ? modes_sum<true>(ex) : modes_sum<false>(ex);
+          if (do_pred && warp == 0 && lane == 0) {
+            const float lse = __fadd_rn(logf(se), mx);
+            if (p.out_logits) p.out_logits[(size_t)s * p.ldo + p.ko_off + k] = lse;
+            if (sharded) {   // the predict epilogue writes the class's cache logit straight into every peer
+              const size_t off = ((size_t)(par * sh.P + R.rank) * 2 + 1) * sh.K_pad + k;
+              for (int r = 0; r < sh.P; ++r) R.peer_recv[r][off] = lse;
+            }
+          }
+        }
+        float rd, g0, cold;
+        {
+          const float lj = lane < M ? __fadd_rn(logpi, __fmul_rn(-0.5f, __fadd_rn(ldet, mf))) : -INFINITY;
+          const float mx = SHORTM ? modes_max<true>(lj) : modes_max<false>(lj);
+          const float ex = lane < M ? expf(__fsub_rn(lj, mx)) : 0.f;
+          const float se = SHORTM ? modes_sum<true>(ex) : modes_sum<false>(ex);
+          const float lse = __fadd_rn(logf(se), mx);
+          // gamma[b=0, mode] = gamma_class * exp(log_joint - logsumexp), the reference's form (dota_mixture.py:182-186);
+          // both fits use the ORIGINAL prob_map (Uni_Adapter.py:417,430)
+          const float gam = lane < M ? __fmul_rn(cur_g, expf(__fsub_rn(lj, lse))) : 0.f;
+          const float cnew = __fadd_rn(c_cur, gam);
+          const float rden = rcp_rn_normal(__fadd_rn(cnew, 1e-10f));
+          const float cm = lane < M ? cnew : 0.f;
+          const float ck = SHORTM ? modes_sum<true>(cm) : modes_sum<false>(cm);
+          cold = __shfl_sync(kFullMask, c_cur, wm);
+          g0 = __shfl_sync(kFullMask, gam, wm);
+          rd = __shfl_sync(kFullMask, rden, wm);
+          c_cur = cnew;
+          pi_cur = __fdiv_rn(cnew, __fadd_rn(ck, 1e-10f));
+          cc_cur = cc_cur + cur_g;
+        }
+        // ---- M-step on the registers of this warp's (mode, chunk) ---------------------------------------------------
 #pragma unroll
         for (int v = 0; v < V; ++v) {
           float mm[4] = {mu4[v].x, mu4[v].y, mu4[v].z, mu4[v].w};
           float vv[4] = {var4[v].x, var4[v].y, var4[v].z, var4[v].w};
-          const float4 t = __ldg(reinterpret_cast<const float4*>(x2_row + 128 * v));
+          const float4 t = rows_smem ? *reinterpret_cast<const float4*>(xrow + 128 * v)
+                                     : __ldg(reinterpret_cast<const float4*>(xrow + 128 * v));
           const float ff[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float wx = __fmul_rn(g2, ff[q]);
-            const float wxsq = __fmul_rn(g2, __fmul_rn(ff[q], ff[q]));
+            const float wx = __fmul_rn(g0, ff[q]);
+            const float wxsq = __fmul_rn(g0, __fmul_rn(ff[q], ff[q]));
             const float mu_ = mm[q];
-            mm[q] = __fmul_rn(__fadd_rn(__fmul_rn(cold2, mu_), wx), rd2);
+            mm[q] = __fmul_rn(__fadd_rn(__fmul_rn(cold, mu_), wx), rd);
             const float term2 = __fmul_rn(__fmul_rn(-2.0f, mu_), wx);
-            const float term3 = __fmul_rn(g2, __fmul_rn(mu_, mu_));
+            const float term3 = __fmul_rn(g0, __fmul_rn(mu_, mu_));
             const float wsd = __fadd_rn(__fadd_rn(wxsq, term2), term3);
-            vv[q] = fmaxf(__fmul_rn(__fadd_rn(__fmul_rn(cold2, vv[q]), wsd), rd2), 1e-8f);
+            vv[q] = fmaxf(__fmul_rn(__fadd_rn(__fmul_rn(cold, vv[q]), wsd), rd), 1e-8f);
           }
           mu4[v] = make_float4(mm[0], mm[1], mm[2], mm[3]);
           var4[v] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+          if (f == nfit - 1) {   // the class's new state: straight from the registers to HBM, interleaved with the math
+            *reinterpret_cast<float4*>(o_mu + 128 * v) = mu4[v];
+            *reinterpret_cast<float4*>(o_var + 128 * v) = var4[v];
+          }
         }
       }
-      // ---- the class's new state: straight from the registers to HBM -----------------------------------------------
       if (warp == 0) {
         if (lane < M) {
-          p.c[(size_t)item * M + lane] = c_out;
-          p.pi[(size_t)item * M + lane] = pi_out;
+          p.c[(size_t)item * M + lane] = c_cur;
+          p.pi[(size_t)item * M + lane] = pi_cur;
         }
-        if (lane == 0) p.class_counts[item] = cc_out;
-      }
-      float* o_mu = p.mu + (size_t)item * MD + (size_t)wm * D + d0;
-      float* o_var = p.var + (size_t)item * MD + (size_t)wm * D + d0;
-#pragma unroll
-      for (int v = 0; v < V; ++v) {
-        *reinterpret_cast<float4*>(o_mu + 128 * v) = mu4[v];
-        *reinterpret_cast<float4*>(o_var + 128 * v) = var4[v];
+        if (lane == 0) p.class_counts[item] = cc_cur;
       }
     }
   } else if (tid == 0) {
@@ -576,12 +542,14 @@ Plan make_plan(int M, int D, size_t extra_smem) {
   static const int kV[] = {1, 2, 4, 5, 8, 10};
   Plan pl;
   for (int gtry = 2; gtry >= 1 && !pl.V; --gtry) {
+    if (g_sample_g > 0 && gtry != g_sample_g) continue;
     for (int i = 5; i >= 0 && !pl.V; --i) {
       const int cand = kV[i];
+      if (g_sample_v > 0 && cand != g_sample_v) continue;
       if (D % (128 * cand)) continue;
       const int thr = gtry * 32 * M * (D / (128 * cand));
       if (thr > s_max_threads(cand, gtry) || thr > 1024) continue;
-      if (gtry == 2 && thr < 256) continue;   // too few warps to hide anything
+      if (gtry == 2 && thr < 256 && !g_sample_g) continue;   // too few warps to hide anything
       pl.V = cand, pl.G = gtry, pl.threads = thr;
     }
   }
@@ -653,7 +621,7 @@ extern "C" int ua_modedota_sample_step_f32(const float* x_fit, const float* x_fi
   UA_UNSUPPORTED(((uintptr_t)mu | (uintptr_t)var | (uintptr_t)x_fit | (uintptr_t)x_fit2) & 15,
                  "ua_modedota_sample_step_f32: pointers must be 16-byte aligned");
   UA_UNSUPPORTED((long long)S * K > 0x3fffffffLL, "ua_modedota_sample_step_f32: S*K too large");
-  const Plan pl = make_plan(M, D, 0);
+  const Plan pl = make_plan(M, D, (size_t)3 * D * sizeof(float) + 16);
   UA_UNSUPPORTED(!pl.V, "ua_modedota_sample_step_f32: no register tiling for M=%d D=%d", M, D);
   LaunchParams lp = {};
   RankParams& r = lp.r[0];
@@ -687,7 +655,7 @@ extern "C" int ua_modedota_sharded_step_f32(const ua_shard_rank* ranks, int n_ra
              K_pad);
   UA_UNSUPPORTED(M > kMaxM || D % 128 != 0, "ua_modedota_sharded_step_f32: needs M <= %d and D %% 128 == 0 (M=%d D=%d)", kMaxM,
                  M, D);
-  const Plan pl = make_plan(M, D, (size_t)K * sizeof(float));
+  const Plan pl = make_plan(M, D, (size_t)(K + 3 * D) * sizeof(float) + 16);
   UA_UNSUPPORTED(!pl.V || pl.threads < P, "ua_modedota_sharded_step_f32: no register tiling for M=%d D=%d K=%d", M, D, K);
   UA_UNSUPPORTED((size_t)K * sizeof(float) > (size_t)pl.NS * 2 * M * D * sizeof(float),
                  "ua_modedota_sharded_step_f32: K=%d too large for the fusion scratch", K);

@@ -320,9 +320,7 @@ class DotaEngine:
         self.final.copy_(final)
         self.pred.copy_(arg)
 
-    def step(self, pc_host: torch.Tensor):
-        """pc_host (1,N,3) pinned host tensor -> (final_logits (1,K) pinned host, pred (1,) device)."""
-        self.pc.copy_(pc_host, non_blocking=True)
+    def _run(self):
         if self.use_graph and self.step_idx >= 2:
             if self.graph is None:
                 self.graph = torch.cuda.CUDAGraph()
@@ -332,6 +330,109 @@ class DotaEngine:
         else:
             self._body()
         self.step_idx += 1
+
+    def step(self, pc_host: torch.Tensor):
+        """pc_host (1,N,3) pinned host tensor -> (final_logits (1,K) pinned host, pred (1,) device)."""
+        self.pc.copy_(pc_host, non_blocking=True)
+        self._run()
         self._host_out.copy_(self.final, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return self._host_out, self.pred
+
+    def step_device(self, pc_dev: torch.Tensor):
+        """Same step with the cloud already resident in HBM; results stay on the device."""
+        self.pc.copy_(pc_dev)
+        self._run()
+        return self.final, self.pred
+
+
+class ShardedSampleEngine:
+    """BASELINE cfg 4 as a product path: ONE stream whose MODE-DOTA cache is sharded by class over the ranks of the
+    process group (Objaverse-LVIS: 1156 classes x 8 modes x 1024 dims = 76 MB of state, split into contiguous class
+    ranges). Every rank runs the (replicated) tokenizer + encoder on the same sample and its jittered view, then the fused
+    class-sharded step (``parallel.FusedShardedModeDota``: local zero-shot logits -> exchange over NVLink -> predict + two
+    fits on the local classes -> exchange -> fusion, one kernel). The whole per-sample step is one CUDA-graph replay.
+    With one rank (or no process group) the same code runs unsharded (P = 1).
+
+    The jitter noise and the FPS start indices come from the stream's counter-based generator (``seed + stream_id``): every
+    rank draws the same values without communicating."""
+
+    def __init__(self, encoder, vlm3d, text, npoints, cfg, mode_M=8, device='cuda', use_graph=True, seed=42, stream_id=0,
+                 emulate_world=None):
+        from .parallel import FusedShardedModeDota
+        import torch.distributed as dist
+        self.dev = torch.device(device)
+        self.encoder, self.vlm3d, self.cfg = encoder, vlm3d, cfg
+        text = text.to(self.dev).float().contiguous()
+        self.K, self.D = text.shape
+        self.N = npoints
+        if emulate_world is None and not (dist.is_available() and dist.is_initialized()):
+            emulate_world = 1
+        self.sharded = FusedShardedModeDota(cfg, text, mode_M, self.dev, emulate_world=emulate_world, use_graph=False)
+        self.pc = torch.zeros(1, npoints, 3, device=self.dev)
+        self.rgb = torch.ones(1, npoints, 3, device=self.dev)
+        self.random_start = vlm3d in ('ulip', 'openshape')
+        self.stream_seeds = torch.tensor([seed + int(stream_id)], dtype=torch.int64, device=self.dev)
+        self.rng_step = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self._rng_done = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.noise_buf = torch.zeros(1, npoints, 3, device=self.dev)
+        self.start_buf = torch.zeros(2, 1, dtype=torch.int64, device=self.dev)
+        self.use_graph, self.graph, self.step_idx = use_graph, None, 0
+        self._host_out = torch.empty(1, self.K, dtype=torch.float32).pin_memory()
+
+    @property
+    def final(self):
+        return self.sharded.mine.out_final
+
+    @property
+    def pred(self):
+        return self.sharded.mine.out_argmax
+
+    @torch.no_grad()
+    def _body(self):
+        rc = _lib.lib().ua_stream_rng_f32(_lib.ptr(self.stream_seeds), _lib.ptr(self.rng_step), 1, self.N * 3,
+                                          _lib.ptr(self.noise_buf), _lib.ptr(self.start_buf), self.N,
+                                          _lib.ptr(self._rng_done), _lib.stream_ptr())
+        _lib.check(rc, "ua_stream_rng_f32")
+        pc2 = torch.cat((self.pc, self.pc + 0.05 * self.noise_buf), dim=0)          # Uni_Adapter.py:420-421
+        rgb2 = torch.cat((self.rgb, self.rgb), dim=0)
+        if self.random_start:
+            for mod in self.encoder.modules():
+                if hasattr(mod, 'next_start_idx'):
+                    mod.next_start_idx = self.start_buf.view(-1)
+        if self.vlm3d == 'uni3d':
+            emb = self.encoder.encode_pc(torch.cat((pc2, rgb2), dim=-1))
+        elif self.vlm3d == 'ulip':
+            emb = self.encoder(pc2)
+        else:
+            emb = self.encoder(pc2, torch.cat((pc2, rgb2), dim=-1))
+        self.sharded.enqueue(emb)
+
+    def _run(self):
+        if self.use_graph and self.step_idx >= 2:
+            if self.graph is None:
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph):
+                    self._body()
+            self.graph.replay()
+        else:
+            self._body()
+        self.step_idx += 1
+
+    def step(self, pc_host: torch.Tensor, rgb_host: torch.Tensor | None = None):
+        """pc_host (1,N,3) pinned host tensor -> (final_logits (1,K) pinned host, pred (1,) device); copies included."""
+        self.pc.copy_(pc_host, non_blocking=True)
+        if rgb_host is not None:
+            self.rgb.copy_(rgb_host, non_blocking=True)
+        self._run()
+        self._host_out.copy_(self.final, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self._host_out, self.pred
+
+    def step_device(self, pc_dev: torch.Tensor):
+        self.pc.copy_(pc_dev)
+        self._run()
+        return self.final, self.pred
+
+    def check(self):
+        self.sharded.check()

@@ -358,6 +358,17 @@ class FusedShardedModeDota:
         _lib.check(rc, "ua_modedota_sharded_step_f32")
 
     @torch.no_grad()
+    def enqueue(self, feats2: torch.Tensor) -> ShardedStepOutput:
+        """Enqueue one step on the current stream without any graph handling of its own (for callers that capture a
+        larger graph around it, ``engine.ShardedSampleEngine``): feats2 (2,D) = raw features of the sample and of its view."""
+        for r in self.ranks:
+            r.x2.copy_(feats2.reshape(2, -1), non_blocking=True)
+        self._launch()
+        self.steps += 1
+        m = self.mine
+        return ShardedStepOutput(m.out_final, m.out_argmax, m.out_clip, m.out_dota)
+
+    @torch.no_grad()
     def step(self, feats_raw: torch.Tensor, feats_aug_raw: torch.Tensor) -> ShardedStepOutput:
         """feats_raw / feats_aug_raw (1,D): raw encoder outputs of the sample and of its jittered view (the same on every
         rank). Returns the replicated result of this rank (static buffers, overwritten by the next step)."""
