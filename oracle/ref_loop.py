@@ -14,12 +14,25 @@ CPU implementation timed on the GPU box's host cores, ``kind: "reference"``). Th
 """
 from __future__ import annotations
 
+import contextlib
 import types
 
 import torch
 import torch.nn.functional as F
 
 from . import reference_loader as R
+
+
+@contextlib.contextmanager
+def cpu_only():
+    """The reference picks its device with ``torch.cuda.is_available()`` (dota.py:24, dota_mixture.py:31): on the GPU box the
+    CPU arm must hide the GPU from it, or the adapter state lands on cuda:0 while the features are on the host."""
+    orig = torch.cuda.is_available
+    torch.cuda.is_available = lambda: False
+    try:
+        yield
+    finally:
+        torch.cuda.is_available = orig
 
 
 def ulip_reference_model(depth: int, seed: int):
@@ -53,19 +66,24 @@ class ReferenceStream:
         self.args = types.SimpleNamespace(vlm3d=vlm3d)
         K = text.shape[0]
         self.use_mode = mode_M > 0
-        if self.use_mode:
-            self.adapter = R.dota_mixture().DOTA_mix(cfg, feat_dim, K, text.t().contiguous(), num_modes=mode_M)
-        else:
-            self.adapter = R.dota().DOTA(cfg, feat_dim, K, torch.full((feat_dim, K), 0.001))   # Uni_Adapter.py:329-330
+        with cpu_only():
+            if self.use_mode:
+                self.adapter = R.dota_mixture().DOTA_mix(cfg, feat_dim, K, text.t().contiguous(), num_modes=mode_M)
+            else:
+                self.adapter = R.dota().DOTA(cfg, feat_dim, K, torch.full((feat_dim, K), 0.001))   # Uni_Adapter.py:329-330
         self.res_learning = res_learning and self.use_mode
         if self.res_learning:
             self.res = torch.zeros_like(text, requires_grad=True)                               # Uni_Adapter.py:346-352
             self.opt = torch.optim.Adam([self.res], lr=0.001)
         self.i = 0
 
-    @torch.no_grad()
     def step(self, pc, rgb):
         """pc, rgb (1,N,3) -> dict(final, clip_logits, dota_logits) (and the adapter advanced by one sample)."""
+        with cpu_only():
+            return self._step(pc, rgb)
+
+    @torch.no_grad()
+    def _step(self, pc, rgb):
         ua, cfg, adapter, text = self.ua, self.cfg, self.adapter, self.text
         feature = torch.cat((pc, rgb), dim=-1)
         if self.res_learning:

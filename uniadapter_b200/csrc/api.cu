@@ -11,6 +11,7 @@ static std::atomic<int64_t> g_launches{0};
 
 extern int g_fps_threads;
 extern int g_dota_ksplit;
+extern int g_dota_staged;
 extern int g_fps_cluster;
 extern int g_knn_warps;
 extern int g_knn_hist;
@@ -55,6 +56,7 @@ extern "C" void ua_reset_launch_count(void) { ua::g_launches.store(0); }
 extern "C" int ua_set_tuning(const char* key, int value) {
   if (!key) return UA_ERR_INVALID_ARG;
   if (!strcmp(key, "fps_threads")) { ua::g_fps_threads = value; return UA_OK; }
+  if (!strcmp(key, "dota_staged")) { ua::g_dota_staged = value; return UA_OK; }
   if (!strcmp(key, "dota_ksplit")) { ua::g_dota_ksplit = value; return UA_OK; }
   if (!strcmp(key, "fps_cluster")) { ua::g_fps_cluster = value; return UA_OK; }
   if (!strcmp(key, "knn_warps")) { ua::g_knn_warps = value; return UA_OK; }

@@ -6,12 +6,14 @@
 // (overall_Sigma) on the fly, so neither delta (K,D,D) nor a second pass for the mean ever touch memory.
 #include <cooperative_groups.h>
 #include "common.cuh"
+#include "modedota_params.cuh"
 
 namespace cg = cooperative_groups;
 
 namespace ua {
 
 int g_dota_ksplit = 0;   // tuning: class splits (cluster size) of the fit kernel, 0 = heuristic
+int g_dota_staged = 1;   // tuning: 0 disables the staged batch-1 kernel (dota_sigma_b1_kernel)
 
 namespace {
 
@@ -104,6 +106,71 @@ __global__ void __launch_bounds__(256)
   const float kf = (float)K;
   float4 m4 = make_float4(__fdiv_rn(mean.x, kf), __fdiv_rn(mean.y, kf), __fdiv_rn(mean.z, kf), __fdiv_rn(mean.w, kf));
   *reinterpret_cast<float4*>(overall + (size_t)i * D + j) = m4;
+}
+
+// Batch-1 fit (the per-sample step of the reference loop, Uni_Adapter.py:411) with everything that is NOT the Sigma stream
+// staged in shared memory first: per class k the tile needs mu_k on its 8 rows and 128 columns, c_k and y_k. The general
+// kernel above fetches them class by class from global memory inside the streaming loop (four dependent small loads and
+// four IEEE divisions per class and thread: 30 us at K = 40, D = 512 for 85 MB, issue-active 30 %). Here the CTA first
+// forms, for all K classes,
+//     wi[k][r]  = y_k * (x_i - mu_k[i])          (8 rows)
+//     dj[k][c]  = x_j - mu_k[j]                  (128 columns)
+//     sc[k]     = { c_k, 1 / (c_k + y_k) }       (one correctly-rounded reciprocal instead of four divisions)
+// (K * 138 floats: 22 KB at K = 40), and the loop over the classes is then a pure stream: KA 16-byte loads of Sigma in
+// flight per thread, two shared-memory reads, 16 multiply / add operations with the reference's rounding points
+// (delta = wi * dj, out = (c_k * Sigma + delta) * rcp), one 16-byte store, the class mean accumulated on the fly.
+template <int KA>
+__global__ void __launch_bounds__(256)
+    dota_sigma_b1_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ mu,
+                         const float* __restrict__ c, float* __restrict__ Sigma, float* __restrict__ overall, int K, int D) {
+  extern __shared__ __align__(16) float s_dyn[];
+  float* s_dj = s_dyn;                                  // [K][128]
+  float* s_wi = s_dj + (size_t)K * kTileCols;           // [K][8]
+  float2* s_sc = reinterpret_cast<float2*>(s_wi + (size_t)K * kTileRows);   // [K]
+  const int t = threadIdx.y * 32 + threadIdx.x;
+  const int j0 = blockIdx.x * kTileCols, i0 = blockIdx.y * kTileRows;
+  for (int idx = t; idx < K * kTileCols; idx += 256) {
+    const int k = idx / kTileCols, col = idx - k * kTileCols, jj = j0 + col;
+    s_dj[idx] = jj < D ? __fsub_rn(__ldg(x + jj), __ldg(mu + (size_t)k * D + jj)) : 0.f;
+  }
+  for (int idx = t; idx < K * kTileRows; idx += 256) {
+    const int k = idx / kTileRows, r = idx - k * kTileRows, ii = i0 + r;
+    s_wi[idx] = ii < D ? __fmul_rn(__ldg(y + k), __fsub_rn(__ldg(x + ii), __ldg(mu + (size_t)k * D + ii))) : 0.f;
+  }
+  for (int k = t; k < K; k += 256) {
+    const float ck = __ldg(c + k);
+    s_sc[k] = make_float2(ck, rcp_rn_normal(__fadd_rn(ck, __ldg(y + k))));
+  }
+  __syncthreads();
+  const int j = j0 + threadIdx.x * 4, i = i0 + threadIdx.y;
+  if (i >= D || j >= D) return;
+  const size_t DD = (size_t)D * D;
+  float* sp = Sigma + (size_t)i * D + j;
+  float4 mean = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto update_class = [&](int k, const float4 sg) {
+    const float4 dj = *reinterpret_cast<const float4*>(s_dj + (size_t)k * kTileCols + threadIdx.x * 4);
+    const float wi = s_wi[k * kTileRows + threadIdx.y];
+    const float2 sc = s_sc[k];
+    float4 out;
+    out.x = __fmul_rn(__fadd_rn(__fmul_rn(sc.x, sg.x), __fmul_rn(wi, dj.x)), sc.y);
+    out.y = __fmul_rn(__fadd_rn(__fmul_rn(sc.x, sg.y), __fmul_rn(wi, dj.y)), sc.y);
+    out.z = __fmul_rn(__fadd_rn(__fmul_rn(sc.x, sg.z), __fmul_rn(wi, dj.z)), sc.y);
+    out.w = __fmul_rn(__fadd_rn(__fmul_rn(sc.x, sg.w), __fmul_rn(wi, dj.w)), sc.y);
+    __stcs(reinterpret_cast<float4*>(sp + (size_t)k * DD), out);
+    mean.x += out.x, mean.y += out.y, mean.z += out.z, mean.w += out.w;
+  };
+  int k = 0;
+  for (; k + KA <= K; k += KA) {
+    float4 sg[KA];
+#pragma unroll
+    for (int u = 0; u < KA; ++u) sg[u] = __ldcs(reinterpret_cast<const float4*>(sp + (size_t)(k + u) * DD));
+#pragma unroll
+    for (int u = 0; u < KA; ++u) update_class(k + u, sg[u]);
+  }
+  for (; k < K; ++k) update_class(k, __ldcs(reinterpret_cast<const float4*>(sp + (size_t)k * DD)));
+  const float kf = (float)K;
+  *reinterpret_cast<float4*>(overall + (size_t)i * D + j) =
+      make_float4(__fdiv_rn(mean.x, kf), __fdiv_rn(mean.y, kf), __fdiv_rn(mean.z, kf), __fdiv_rn(mean.w, kf));
 }
 
 // mu' = (y^T x + c*mu) / (s + c), c' = c + s   (run after the Sigma kernel, which needs the old mu and c)
@@ -215,7 +282,12 @@ extern "C" int ua_dota_fit_f32(const float* x, const float* y, int B, float* mu,
   int KS = g_dota_ksplit > 0 ? g_dota_ksplit : 1;
   if (KS > K) KS = 1;
   dim3 grid((D + kTileCols - 1) / kTileCols, (D + kTileRows - 1) / kTileRows, KS), block(32, kTileRows);
-  if (KS == 1) {
+  const size_t staged_smem = (size_t)K * (kTileCols + kTileRows + 2) * sizeof(float);
+  if (B == 1 && g_dota_staged && KS == 1 && staged_smem <= 96 * 1024) {
+    auto kern = dota_sigma_b1_kernel<8>;
+    if (staged_smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged_smem);
+    kern<<<dim3(grid.x, grid.y), block, staged_smem, st>>>(x, y, mu, c, Sigma, overall, K, D);
+  } else if (KS == 1) {
     dota_sigma_kernel<<<grid, block, 0, st>>>(x, y, B, mu, c, Sigma, overall, K, D);
   } else {
     cudaLaunchConfig_t cfg = {};

@@ -31,12 +31,12 @@ constexpr float kFpsInit = 1e10f;
 // pointnet2_ops tie order. Upstream thread t = k mod bs owns point k and keeps its FIRST maximum; the pairwise tree
 // (t, t + bs/2), (t, t + bs/4), ... (0, 1) keeps the LEFT operand on ties, so among equal maxima the winner is the thread
 // with the smallest BIT-REVERSED id (the last level lets even threads beat odd ones, the one before decides bit 1, ...):
-// comp(k) = bitrev_lg(k mod bs) * q + k / bs with bs = 2^lg, q = ceil(N / bs); ties go to the lowest comp.
+// comp(k) = (bitrev_lg(k mod bs), k / bs) packed into one word with bs = 2^lg; ties go to the lowest comp.
 struct Pn2Order {
-  int lg, q;
+  int lg, lq;      // bs = 2^lg; 2^lq >= ceil(N / bs): a power of two keeps the (thread, round) order and decodes by shifts
   __device__ __forceinline__ uint32_t rev(uint32_t t) const { return lg ? (__brev(t) >> (32 - lg)) : 0u; }
-  __device__ __forceinline__ uint32_t comp(uint32_t k) const { return rev(k & ((1u << lg) - 1u)) * (uint32_t)q + (k >> lg); }
-  __device__ __forceinline__ uint32_t index(uint32_t c) const { return ((c % (uint32_t)q) << lg) + rev(c / (uint32_t)q); }
+  __device__ __forceinline__ uint32_t comp(uint32_t k) const { return (rev(k & ((1u << lg) - 1u)) << lq) | (k >> lg); }
+  __device__ __forceinline__ uint32_t index(uint32_t c) const { return ((c & ((1u << lq) - 1u)) << lg) + rev(c >> lq); }
 };
 __device__ __forceinline__ float sqdist_pn2(float px, float py, float pz, float cx, float cy, float cz) {
   const float dx = __fsub_rn(px, cx), dy = __fsub_rn(py, cy), dz = __fsub_rn(pz, cz);
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(PPT == 12 ? 896 : 1024, 1)
         }
       }
       uint32_t bestc = best < 0.f ? 0u : ord.comp((uint32_t)(bestj * T + tid));
-      if (__any_sync(kFullMask, tie && best >= 0.f)) {     // rare: several of a thread's points share its maximum
+      if (tie && best >= 0.f) {     // rare (no vote on the critical path): several of this thread's points share its maximum
 #pragma unroll
         for (int j = 0; j < PPT; ++j)
           if (dmin[j] == best && best >= 0.f) bestc = min(bestc, ord.comp((uint32_t)(j * T + tid)));
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(512, 1)
         }
       }
       uint32_t bestc = best < 0.f ? 0u : ord.comp((uint32_t)(n0 + bestj * T + tid));
-      if (__any_sync(kFullMask, tie && best >= 0.f)) {     // rare: several of a thread's points share its maximum
+      if (tie && best >= 0.f) {     // rare (no vote on the critical path): several of this thread's points share its maximum
 #pragma unroll
         for (int j = 0; j < PPT; ++j)
           if (dmin[j] == best && best >= 0.f) bestc = min(bestc, ord.comp((uint32_t)(n0 + j * T + tid)));
@@ -394,7 +394,9 @@ int dispatch(const float* xyz, int B, int N, int G, const int64_t* start_idx, in
   Pn2Order ord;
   ord.lg = 0;
   while ((2 << ord.lg) <= N && (2 << ord.lg) <= 512) ++ord.lg;     // upstream opt_n_threads(N)
-  ord.q = (N + (1 << ord.lg) - 1) >> ord.lg;
+  const int rounds = (N + (1 << ord.lg) - 1) >> ord.lg;
+  ord.lq = 0;
+  while ((1 << ord.lq) < rounds) ++ord.lq;
   if (N > UA_FPS_MAX_REG_POINTS) {
     UA_UNSUPPORTED(PN2, "ua_fps_f32: the pointnet2_ops arithmetic is implemented for N <= %d", UA_FPS_MAX_REG_POINTS);
     UA_REQUIRE(scratch != nullptr, "ua_fps_f32: N=%d > %d needs a [B,N] f32 scratch", N, UA_FPS_MAX_REG_POINTS);
