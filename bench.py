@@ -518,29 +518,38 @@ def sharded_step_probe(cfg, dev, flush):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.barrier()
 
-    ts = []
     g = torch.cuda.CUDAGraph()
     fused.enqueue(emb)
     sync_all()
     with torch.cuda.graph(g):
         fused.enqueue(emb)
-    for _ in range(15):
-        flush.zero_()
+
+    def chain(n, with_step):
+        """n x [L2 flush, step] queued back to back (no host synchronisation in between: the ranks pace one another
+        through the exchange itself, as they do in the real loop), device time of the whole chain."""
         sync_all()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda._sleep(400000)
+        torch.cuda._sleep(2000000)
         s.record()
-        g.replay()
+        for _ in range(n):
+            flush.zero_()
+            if with_step:
+                g.replay()
         e.record()
         torch.cuda.synchronize()
-        ts.append(s.elapsed_time(e) * 1e3)
+        return s.elapsed_time(e) * 1e3
+
+    n = 20
+    chain(3, True)
+    per_step = sorted((chain(n, True) - chain(n, False)) / n for _ in range(3))[1]
     fused.check()
-    t = torch.tensor([sorted(ts)[len(ts) // 2]], device=dev)
+    t = torch.tensor([per_step], device=dev)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     out = {"world": cfg.world, "classes_per_rank": fused.mine.Kp, "fused_sharded_adapter_step_us": round(float(t), 2),
            "what": "ua_head_f32 on the local text rows + ua_modedota_sharded_step_f32 (exchange, predict + 2 fits, exchange, "
-                   "fusion), one CUDA-graph replay, median of 15, max over ranks, L2 flushed"}
+                   "fusion) as one CUDA-graph replay; 20 x [L2 flush, step] queued back to back minus 20 x [L2 flush], per "
+                   "step, median of 3, max over ranks (steady state: no host-side start skew between the ranks)"}
     # single-GPU adapter step for comparison (every rank measures it locally; rank 0's figure is reported)
     text = cfg.text.to(dev)
     full = ua.DOTA_mix(CFG, D, K, text.t().contiguous(), num_modes=M, device=dev)

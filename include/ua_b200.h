@@ -270,14 +270,18 @@ int ua_modedota_sample_step_f32(const float* x_fit, const float* x_fit2, const f
  * The reference has no multi-GPU path; this is the exchange step the north star names (logit all-gather per step),
  * done with stores into NVLink-mapped peer memory from the kernel itself instead of a collective call.
  * Class ranges are contiguous, the first K mod P ranks own one class more. Every rank passes the same sample.
- *   per rank (struct below, a HOST array of n_ranks entries, copied into the kernel parameters): the normalised sample / jittered view, its zero-shot logits
- *   clip_local [K_local] (ua_head_f32 on its text rows), its state shard, and
+ *   per rank (struct below, a HOST array of n_ranks entries, copied into the kernel parameters):
+ *     text_local [K_local, D] != NULL: x_fit / x_fit2 [D] are the RAW encoder outputs of the sample and of its jittered
+ *       view (x_fit2 may be NULL); the kernel L2-normalises them and forms the zero-shot logits of its classes itself
+ *       (the arithmetic of ua_head_f32, Uni_Adapter.py:56-57) -- the whole adapter step is this one launch;
+ *     text_local == NULL: x_fit / x_fit2 are already normalised and clip_local [K_local] holds the zero-shot logits;
+ *     the state shard (mu, var, pi, c, class_counts over K_local classes), and
  *     peer_recv: device array [P] of float* -- every rank's symmetric receive buffer, 2*P*2*K_pad floats
  *                ([parity][rank][0: zero-shot | 1: cache][K_pad]), mapped into this process;
  *     peer_flag: device array [P] of int* -- every rank's 2*P flags ([exchange][rank]), zero-initialised;
  *     seq (device int, step counter, advanced by the kernel; all ranks start from 0), err (device int: 1 = a peer's
  *     zero-shot logits did not arrive, cache untouched; 2 = a peer's cache logits did not arrive or the peer aborted;
- *     outputs are NaN / -1 then), done (zeroed u32 scratch), c_sum (device float: sum of the soft counts so far, K at
+ *     outputs are NaN / -1 then), done (TWO zeroed u32 of scratch), c_sum (device float: sum of the soft counts so far, K at
  *     start; the kernel adds the fits of the step -- closed form);
  *     out_final [K], out_argmax [1], out_clip / out_dota [K] or NULL: replicated results of the step.
  *   n_ranks = 1: this process' rank (ONE struct). n_ranks = P <= 8: single-GPU emulation of all P ranks in one
@@ -287,6 +291,7 @@ int ua_modedota_sample_step_f32(const float* x_fit, const float* x_fit2, const f
 typedef struct ua_shard_rank {
   const float* x_fit;
   const float* x_fit2;
+  const float* text_local;
   const float* clip_local;
   float* mu;
   float* var;
@@ -306,6 +311,8 @@ typedef struct ua_shard_rank {
   int rank;
   int reserved;
 } ua_shard_rank;
+/* diagnosis: phase time stamps (ns) of the last sharded step launched with ua_set_tuning("sample_trace", 1) */
+int ua_debug_sample_trace(int64_t* host_out16);
 int ua_modedota_sharded_step_f32(const ua_shard_rank* ranks, int n_ranks, int P, int K, int K_pad, int M, int D,
                                  float eps, float rho, float eta, void* stream);
 

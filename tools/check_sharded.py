@@ -114,10 +114,46 @@ if world > 1 and os.environ.get("UA_SHARDED_NCCL", "1") == "1":
             t_nccl.append(us)
         ok &= int(o.pred) == ref[t][1]
 
+# ---- steady-state device time per step: n x [L2 flush, step] queued back to back minus n x [L2 flush] ------------------
+def flush_():
+    _flush_w.zero_()
+    _sink.copy_(_flush_r.sum())
+
+
+def chain(fn, n):
+    torch.cuda.synchronize()
+    dist.barrier()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda._sleep(2000000)
+    s.record()
+    for i in range(n):
+        flush_()
+        if fn is not None:
+            fn(i)
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) * 1e3
+
+
+def steady(fn, n=20):
+    chain(fn, 3)
+    v = sorted((chain(fn, n) - chain(None, n)) / n for _ in range(3))[1]
+    t = torch.tensor([v], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return round(float(t), 2)
+
+
+steady_fused = steady(lambda i: fused.step(x[i % T], xa[i % T]))
+fused.check()
+steady_single = steady(lambda i: graph.replay())
+steady_nccl = steady(lambda i: shard.step_graphed(x[i % T], xa[i % T])) if t_nccl else None
+
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 res = {"check": "class_sharded_modedota", "world": world, "K": K, "M": M, "D": D, "classes_per_rank": m.k_hi - m.k_lo,
        "all_ranks_match_unsharded": bool(flag.item()),
+       "steady_state_us_per_step": {"fused": steady_fused, "nccl_two_graphs": steady_nccl, "single_gpu_unsharded": steady_single,
+                                    "how": "20 x [L2 flush, step] queued back to back minus 20 x [L2 flush], median of 3, max over ranks"},
        "fused_step_us_median_max_over_ranks": med_max(t_fused),
        "nccl_two_graph_step_us_median_max_over_ranks": med_max(t_nccl) if t_nccl else None,
        "single_gpu_unsharded_step_us_median": med_max(t_single),

@@ -40,6 +40,7 @@ SIGNATURES = {
     "ua_row_stats_f32": (_I, [_P, _I, _I, C.c_longlong, _P, _P, _P, _P]),
     "ua_modedota_step_f32": (_I, [_P, _I, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _I, _I, _P]),
     "ua_modedota_sample_step_f32": (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _I, _I, _P]),
+    "ua_debug_sample_trace": (_I, [_P]),
     "ua_modedota_sharded_step_f32": (_I, [_P, _I, _I, _I, _I, _I, _I, _F, _F, _F, _P]),
     "ua_fuse_logits_f32": (_I, [_P, _P, _I, _I, _I, _P, _I, _I, _F, _F, _F, _F, _F, _I, _P, _P, _P, _P]),
     "ua_stream_rng_f32": (_I, [_P, _P, _I, C.c_longlong, _P, _P, _I, _P, _P]),
@@ -66,7 +67,7 @@ SIGNATURES = {
 
 class ShardRank(C.Structure):
     """``ua_shard_rank`` of include/ua_b200.h (a host array; the library copies it into the kernel parameters)."""
-    _fields_ = [("x_fit", _P), ("x_fit2", _P), ("clip_local", _P), ("mu", _P), ("var", _P), ("pi", _P), ("c", _P),
+    _fields_ = [("x_fit", _P), ("x_fit2", _P), ("text_local", _P), ("clip_local", _P), ("mu", _P), ("var", _P), ("pi", _P), ("c", _P),
                 ("class_counts", _P), ("peer_recv", _P), ("peer_flag", _P), ("seq", _P), ("err", _P), ("done", _P),
                 ("c_sum", _P), ("out_final", _P), ("out_argmax", _P), ("out_clip", _P), ("out_dota", _P), ("rank", _I),
                 ("reserved", _I)]

@@ -26,6 +26,8 @@ extern int g_modedota_batch;
 extern int g_p2p_timeout_ms;
 extern int g_sample_v;
 extern int g_sample_g;
+extern int g_sample_skip;
+extern int g_sample_trace_on;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -70,6 +72,8 @@ extern "C" int ua_set_tuning(const char* key, int value) {
   if (!strcmp(key, "modedota_logprod")) { ua::g_modedota_logprod = value; return UA_OK; }
   if (!strcmp(key, "modedota_batch")) { ua::g_modedota_batch = value; return UA_OK; }
   if (!strcmp(key, "sample_v")) { ua::g_sample_v = value; return UA_OK; }
+  if (!strcmp(key, "sample_trace")) { ua::g_sample_trace_on = value; return UA_OK; }
+  if (!strcmp(key, "sample_skip")) { ua::g_sample_skip = value; return UA_OK; }
   if (!strcmp(key, "sample_g")) { ua::g_sample_g = value; return UA_OK; }
   if (!strcmp(key, "p2p_timeout_ms")) { ua::g_p2p_timeout_ms = value; return UA_OK; }
   ua::set_error("ua_set_tuning: unknown key '%s'", key);

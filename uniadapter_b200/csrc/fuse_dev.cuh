@@ -28,6 +28,28 @@ __device__ __forceinline__ float block_max(float v, float* s_tmp) {
   return t;
 }
 
+// pair versions (same per-value order as block_sum / block_max): s_tmp needs 64 floats
+__device__ __forceinline__ void block_sum2(float& a, float& b, float* s_tmp) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+  a = warp_sum(a), b = warp_sum(b);
+  __syncthreads();
+  if (lane == 0) s_tmp[warp] = a, s_tmp[32 + warp] = b;
+  __syncthreads();
+  float ta = 0.f, tb = 0.f;
+  for (int w = 0; w < W; ++w) ta += s_tmp[w], tb += s_tmp[32 + w];
+  a = ta, b = tb;
+}
+__device__ __forceinline__ void block_max2(float& a, float& b, float* s_tmp) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+  a = warp_max(a), b = warp_max(b);
+  __syncthreads();
+  if (lane == 0) s_tmp[warp] = a, s_tmp[32 + warp] = b;
+  __syncthreads();
+  float ta = -INFINITY, tb = -INFINITY;
+  for (int w = 0; w < W; ++w) ta = fmaxf(ta, s_tmp[w]), tb = fmaxf(tb, s_tmp[32 + w]);
+  a = ta, b = tb;
+}
+
 // -sum softmax(v) * log(softmax(v) + 1e-10) over K entries produced by `get(k)`
 template <typename F>
 __device__ __forceinline__ float softmax_entropy(F get, int K, float* s_tmp) {

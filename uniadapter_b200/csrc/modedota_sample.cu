@@ -37,8 +37,21 @@ namespace ua {
 int g_p2p_timeout_ms = 2000;   // tuning: bound of every in-kernel wait for a peer
 int g_sample_v = 0;            // tuning override: float4s per lane (0 = heuristic)
 int g_sample_g = 0;            // tuning override: warp groups per CTA (0 = heuristic)
+int g_sample_skip = 0;         // diagnosis only: bit 0 skips the class loop, bit 1 the fusion (timing of the phases)
+
+// diagnosis: phase time stamps (globaltimer, ns) of rank 0's CTA 0 (slots 0-7) and of its last CTA (slots 8-15)
+__device__ long long g_sample_trace[16];
+int g_sample_trace_on = 0;
 
 namespace {
+
+__device__ __forceinline__ void trace(int on, int slot) {
+  if (on && threadIdx.x == 0) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_sample_trace[slot] = t;
+  }
+}
 
 constexpr int kMaxLaunchRanks = 8;   // ranks emulated by one launch (tests); a real rank launches exactly one
 
@@ -52,7 +65,8 @@ struct RankParams {
   float *mu, *var, *pi, *c, *class_counts;
   float* out_logits;     // [S,ldo] or null
   // sharded form only
-  const float* clip_local;
+  const float* text_local;   // [K_local, D] text rows of this rank: the kernel normalises the rows and forms the zero-shot logits
+  const float* clip_local;   // or: zero-shot logits computed by the caller (x_fit / x_fit2 then hold NORMALISED rows)
   float* const* peer_recv;
   int* const* peer_flag;
   int* seq;
@@ -68,7 +82,7 @@ struct RankParams {
 
 struct LaunchParams {
   RankParams r[kMaxLaunchRanks];
-  int S, M, D, stages, want_pred, sharded, P, Ktot, K_pad;
+  int S, M, D, stages, want_pred, sharded, P, Ktot, K_pad, skip, trace;
   float eps, rho, eta;
   long long timeout_cycles;
 };
@@ -108,11 +122,9 @@ __device__ __forceinline__ int ld_volatile_shared(const int* p) {
 __device__ __forceinline__ void st_volatile_shared(int* p, int v) {
   asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
-__device__ __forceinline__ float ld_volatile_f32(const float* p) {
-  float v;
-  asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
-  return v;
-}
+// data written by a peer into THIS GPU's memory, read after the acquire of the peer's flag: L2 is the point of coherence,
+// so an L1-bypassing load is enough (and, unlike ld.volatile, several of them may be in flight)
+__device__ __forceinline__ float ld_peer_written(const float* p) { return __ldcg(p); }
 __device__ __forceinline__ int ld_acquire_sys(const int* p) {
   int v;
   asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -156,7 +168,7 @@ __global__ void __launch_bounds__(s_max_threads(V, G), 1)
   extern __shared__ __align__(128) unsigned char s_raw[];
   __shared__ int s_flag;
   __shared__ float s_stat[2];
-  __shared__ float s_tmp[32];
+  __shared__ float s_tmp[64];
   __shared__ float s_bestv[32];
   __shared__ unsigned s_besti[32];
   const int tid = threadIdx.x, lane = tid & 31, T = blockDim.x;
@@ -196,7 +208,7 @@ __global__ void __launch_bounds__(s_max_threads(V, G), 1)
 
   const int total = lp.S * p.K;
   const int first = blockIdx.x, stride = gridDim.x;
-  const int n_mine = first < total ? (total - first + stride - 1) / stride : 0;
+  const int n_mine = (first < total && !(lp.skip & 1)) ? (total - first + stride - 1) / stride : 0;
 
   auto item_of = [&](int j) { return first + j * stride; };   // j-th class of this CTA
   auto issue_load = [&](int j) {   // -> stage j % NS
@@ -215,7 +227,42 @@ __global__ void __launch_bounds__(s_max_threads(V, G), 1)
     fence_mbar_init();
     for (int j = 0; j < NS && j < n_mine; ++j) issue_load(j);   // the first tiles fly while the exchange below runs
   }
-  if (rows_smem) {
+  const int tr0 = lp.trace && blockIdx.x == 0 && blockIdx.y == 0;
+  trace(tr0, 0);
+  const bool own_head = sharded && R.text_local != nullptr;
+  float* s_xs = s_rows + 3 * D;        // [D] scale * xnorm: the left operand of the zero-shot logits (own_head)
+  if (own_head) {
+    // L2-normalise the raw rows exactly as ua_head_f32's l2norm_kernel does (256 threads, strided FMA sums, warp sums,
+    // serial sum over the warps, one division per element), so that the sharded step sees the unsharded step's features
+    const int NT = min(T, 256), NW = NT >> 5;
+    // both raw rows land in shared memory first (all loads in flight together: one DRAM round trip), then the two sums
+    for (int d = tid; d < D; d += T) {
+      s_rows[D + d] = __ldg(p.x_fit + d);
+      s_rows[2 * D + d] = fit2 ? __ldg(p.x_fit2 + d) : 0.f;
+    }
+    __syncthreads();
+    float ss0 = 0.f, ss1 = 0.f;
+    if (tid < NT)
+      for (int d = tid; d < D; d += NT) {
+        const float v0 = s_rows[D + d], v1 = s_rows[2 * D + d];
+        ss0 = fmaf(v0, v0, ss0);
+        ss1 = fmaf(v1, v1, ss1);
+      }
+    ss0 = warp_sum(ss0);
+    ss1 = warp_sum(ss1);
+    if (tid < NT && lane == 0) s_tmp[tid >> 5] = ss0, s_tmp[16 + (tid >> 5)] = ss1;
+    __syncthreads();
+    float tot0 = 0.f, tot1 = 0.f;
+    for (int w = 0; w < NW; ++w) tot0 += s_tmp[w], tot1 += s_tmp[16 + w];
+    const float nrm0 = sqrtf(tot0), nrm1 = sqrtf(tot1);
+    for (int d = tid; d < D; d += T) {
+      const float xn = __fdiv_rn(s_rows[D + d], nrm0);
+      s_rows[d] = __half2float(__float2half_rn(xn));
+      s_rows[D + d] = xn;
+      s_xs[d] = __fmul_rn(100.0f, xn);            // the reference scales x before the contraction (Uni_Adapter.py:57)
+      if (fit2) s_rows[2 * D + d] = __fdiv_rn(s_rows[2 * D + d], nrm1);
+    }
+  } else if (rows_smem) {
     for (int d = tid; d < D; d += T) {
       const float xv = __ldg(p.x_fit + d);
       s_rows[d] = __half2float(__float2half_rn(xv));
@@ -225,10 +272,43 @@ __global__ void __launch_bounds__(s_max_threads(V, G), 1)
   }
   __syncthreads();
 
+  trace(tr0, 1);
   bool ok = true;
   if (sharded) {
-    // ---- A: this rank's zero-shot logits -> every peer (CTA 0) -------------------------------------------------
-    if (blockIdx.x == 0) {
+    // ---- A: this rank's zero-shot logits -> every peer ----------------------------------------------------------
+    if (own_head) {
+      // every CTA forms the logits of ITS classes (one warp per class: lane-strided float4 FMAs + butterfly sum, the
+      // arithmetic of ua_head_f32's logits_kernel) and stores them straight into every peer; a grid-wide counter
+      // elects the CTA that releases the flags
+      const int nwarps_cta = T >> 5, wid = tid >> 5;
+      for (int jj = wid; jj < n_mine; jj += nwarps_cta) {
+        const int k = item_of(jj);
+        const float* trow = R.text_local + (size_t)k * D;
+        float acc = 0.f;
+        for (int d = lane * 4; d < D; d += 128) {
+          const float4 t4 = __ldg(reinterpret_cast<const float4*>(trow + d));
+          const float4 xv = *reinterpret_cast<const float4*>(s_xs + d);
+          acc = fmaf(xv.x, t4.x, acc);
+          acc = fmaf(xv.y, t4.y, acc);
+          acc = fmaf(xv.z, t4.z, acc);
+          acc = fmaf(xv.w, t4.w, acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) {
+          const size_t off = ((size_t)(par * sh.P + R.rank) * 2 + 0) * sh.K_pad + k;
+          for (int r = 0; r < sh.P; ++r) R.peer_recv[r][off] = acc;
+        }
+      }
+      __syncthreads();
+      if (tid == 0) {
+        __threadfence();          // device scope is enough here: the electing CTA below fences at system scope (cumulative)
+        if (atomicAdd(R.done + 1, 1u) == gridDim.x - 1) {
+          R.done[1] = 0u;
+          __threadfence_system();
+          for (int r = 0; r < sh.P; ++r) st_release_sys(R.peer_flag[r] + (0 * sh.P + R.rank), seq);
+        }
+      }
+    } else if (blockIdx.x == 0) {
       for (int r = 0; r < sh.P; ++r) {
         float* dst = R.peer_recv[r] + ((size_t)(par * sh.P + R.rank) * 2 + 0) * sh.K_pad;
         for (int i = tid; i < p.K; i += T) dst[i] = R.clip_local[i];
@@ -237,6 +317,7 @@ __global__ void __launch_bounds__(s_max_threads(V, G), 1)
       __syncthreads();
       if (tid < sh.P) st_release_sys(R.peer_flag[tid] + (0 * sh.P + R.rank), seq);
     }
+    trace(tr0, 2);
     // ---- B: gathered zero-shot row + softmax statistics (every CTA) ---------------------------------------------
     ok = wait_flags(R.peer_flag[R.rank] + 0 * sh.P, sh.P, seq, sh.timeout_cycles, &s_flag);
     if (ok) {
@@ -244,7 +325,7 @@ __global__ void __launch_bounds__(s_max_threads(V, G), 1)
       for (int k = tid; k < sh.K; k += T) {
         int r, i;
         owner_of(k, sh.K, sh.P, r, i);
-        s_clip[k] = ld_volatile_f32(recv + ((size_t)r * 2 + 0) * sh.K_pad + i);
+        s_clip[k] = ld_peer_written(recv + ((size_t)r * 2 + 0) * sh.K_pad + i);
       }
       __syncthreads();
       float mx = -INFINITY;
@@ -259,6 +340,7 @@ __global__ void __launch_bounds__(s_max_threads(V, G), 1)
       atomicExch(R.err, 1);
     }
   }
+  trace(tr0, 3);
   const float sm_max = sharded ? s_stat[0] : 0.f, sm_sum = sharded ? s_stat[1] : 1.f;
 
   if (ok) {
@@ -450,15 +532,18 @@ __global__ void __launch_bounds__(s_max_threads(V, G), 1)
     for (int j = 0; j < NS && j < n_mine; ++j) mbar_wait(&s_bar[j % NS], 0u);
   }
   if (!sharded) return;
+  trace(tr0, 4);
 
   // ---- D: the last CTA of the rank closes exchange 1 and fuses the gathered rows ------------------------------------
   __syncthreads();
   if (tid == 0) {
-    __threadfence_system();          // this CTA's peer stores are visible before its arrival is
+    __threadfence();                 // this CTA's peer stores are ordered before its arrival (the last CTA fences at system scope)
     s_flag = atomicAdd(R.done, 1u) == gridDim.x - 1 ? 1 : 0;
   }
   __syncthreads();
   if (!s_flag) return;
+  const int tr1 = lp.trace && blockIdx.y == 0;
+  trace(tr1, 8);
   if (tid == 0) *R.done = 0u;
   __threadfence_system();
   if (tid < sh.P) st_release_sys(R.peer_flag[tid] + (1 * sh.P + R.rank), ok ? seq : -seq);
@@ -483,22 +568,39 @@ __global__ void __launch_bounds__(s_max_threads(V, G), 1)
     ok2 = s_flag == 0;
   }
   const int K = sh.K;
-  if (ok2) {
+  trace(tr1, 9);
+  if (ok2 && !(lp.skip & 2)) {
     float* s_dota = s_tiles;         // the ring is idle: every load of this CTA has been consumed
     const float* recv = R.peer_recv[R.rank] + (size_t)par * sh.P * 2 * sh.K_pad;
     for (int k = tid; k < K; k += T) {
       int r, i;
       owner_of(k, K, sh.P, r, i);
-      s_dota[k] = ld_volatile_f32(recv + ((size_t)r * 2 + 1) * sh.K_pad + i);
+      s_dota[k] = ld_peer_written(recv + ((size_t)r * 2 + 1) * sh.K_pad + i);
     }
     __syncthreads();
+    trace(tr1, 10);
     // sum(c) in closed form: every fit of a batch-1 sample adds exactly 1
     const float csum = *R.c_sum + (fit2 ? 2.f : 1.f);
     const float w = cache_weight(csum, (float)K * (float)M, sh.rho, 1.f, sh.eta);
-    const float hc = softmax_entropy([&](int k) { return s_clip[k]; }, K, s_tmp);
-    const float hd = softmax_entropy([&](int k) { return __fmul_rn(w, s_dota[k]); }, K, s_tmp);
+    // the two softmax entropies (zero-shot row, scaled cache row) share their passes: three block reductions of a
+    // pair each instead of six (the arithmetic per row is fuse_dev.cuh's softmax_entropy)
+    float mc = -INFINITY, md = -INFINITY;
+    for (int k = tid; k < K; k += T) mc = fmaxf(mc, s_clip[k]), md = fmaxf(md, __fmul_rn(w, s_dota[k]));
+    block_max2(mc, md, s_tmp);
+    float sc = 0.f, sd = 0.f;
+    for (int k = tid; k < K; k += T) sc += expf(s_clip[k] - mc), sd += expf(__fmul_rn(w, s_dota[k]) - md);
+    block_sum2(sc, sd, s_tmp);
+    float ec = 0.f, ed = 0.f;
+    for (int k = tid; k < K; k += T) {
+      const float pc = __fdiv_rn(expf(s_clip[k] - mc), sc), pd = __fdiv_rn(expf(__fmul_rn(w, s_dota[k]) - md), sd);
+      ec += pc * logf(pc + 1e-10f);
+      ed += pd * logf(pd + 1e-10f);
+    }
+    block_sum2(ec, ed, s_tmp);
+    const float hc = -ec, hd = -ed;
     float wc, wd;
     entropy_weights(hc, hd, wc, wd);
+    trace(tr1, 11);
     float best = -INFINITY;
     unsigned besti = 0xffffffffu;
     for (int k = tid; k < K; k += T) {
@@ -528,6 +630,7 @@ __global__ void __launch_bounds__(s_max_threads(V, G), 1)
       atomicExch(R.err, 2);
     }
   }
+  trace(tr1, 12);
   if (tid == 0) *R.seq = seq;
 }
 
@@ -655,7 +758,7 @@ extern "C" int ua_modedota_sharded_step_f32(const ua_shard_rank* ranks, int n_ra
              K_pad);
   UA_UNSUPPORTED(M > kMaxM || D % 128 != 0, "ua_modedota_sharded_step_f32: needs M <= %d and D %% 128 == 0 (M=%d D=%d)", kMaxM,
                  M, D);
-  const Plan pl = make_plan(M, D, (size_t)(K + 3 * D) * sizeof(float) + 16);
+  const Plan pl = make_plan(M, D, (size_t)(K + 4 * D) * sizeof(float) + 16);
   UA_UNSUPPORTED(!pl.V || pl.threads < P, "ua_modedota_sharded_step_f32: no register tiling for M=%d D=%d K=%d", M, D, K);
   UA_UNSUPPORTED((size_t)K * sizeof(float) > (size_t)pl.NS * 2 * M * D * sizeof(float),
                  "ua_modedota_sharded_step_f32: K=%d too large for the fusion scratch", K);
@@ -664,15 +767,15 @@ extern "C" int ua_modedota_sharded_step_f32(const ua_shard_rank* ranks, int n_ra
   for (int i = 0; i < n_ranks; ++i) {
     const ua_shard_rank& h = ranks[i];
     UA_REQUIRE(h.rank >= 0 && h.rank < P, "ua_modedota_sharded_step_f32: rank %d out of range", h.rank);
-    UA_REQUIRE(h.x_fit && h.clip_local && h.mu && h.var && h.pi && h.c && h.class_counts && h.peer_recv && h.peer_flag && h.seq &&
+    UA_REQUIRE(h.x_fit && (h.clip_local || h.text_local) && h.mu && h.var && h.pi && h.c && h.class_counts && h.peer_recv && h.peer_flag && h.seq &&
                    h.err && h.done && h.c_sum && h.out_final && h.out_argmax,
                "ua_modedota_sharded_step_f32: NULL pointer in rank struct %d", i);
-    UA_UNSUPPORTED(((uintptr_t)h.mu | (uintptr_t)h.var | (uintptr_t)h.x_fit | (uintptr_t)h.x_fit2) & 15,
+    UA_UNSUPPORTED(((uintptr_t)h.mu | (uintptr_t)h.var | (uintptr_t)h.x_fit | (uintptr_t)h.x_fit2 | (uintptr_t)h.text_local) & 15,
                    "ua_modedota_sharded_step_f32: pointers must be 16-byte aligned");
     RankParams& r = lp.r[i];
     r.x_fit = h.x_fit, r.x_fit2 = h.x_fit2, r.gamma = nullptr;
     r.mu = h.mu, r.var = h.var, r.pi = h.pi, r.c = h.c, r.class_counts = h.class_counts, r.out_logits = nullptr;
-    r.clip_local = h.clip_local, r.peer_recv = h.peer_recv, r.peer_flag = h.peer_flag;
+    r.text_local = h.text_local, r.clip_local = h.clip_local, r.peer_recv = h.peer_recv, r.peer_flag = h.peer_flag;
     r.seq = h.seq, r.err = h.err, r.done = h.done, r.c_sum = h.c_sum;
     r.out_final = h.out_final, r.out_argmax = h.out_argmax, r.out_clip = h.out_clip, r.out_dota = h.out_dota;
     r.rank = h.rank;
@@ -680,6 +783,7 @@ extern "C" int ua_modedota_sharded_step_f32(const ua_shard_rank* ranks, int n_ra
     r.K = base + (h.rank < extra ? 1 : 0);
   }
   lp.S = 1, lp.M = M, lp.D = D, lp.eps = eps, lp.stages = pl.NS, lp.want_pred = 1;
+  lp.skip = g_sample_skip, lp.trace = g_sample_trace_on;
   lp.sharded = 1, lp.P = P, lp.Ktot = K, lp.K_pad = K_pad, lp.rho = rho, lp.eta = eta;
   lp.timeout_cycles = (long long)g_p2p_timeout_ms * 2000000LL;      // ~2 GHz
   int gx = kNumSMs / n_ranks;
@@ -693,4 +797,8 @@ extern "C" int ua_modedota_sharded_step_f32(const ua_shard_rank* ranks, int n_ra
     return UA_ERR_CUDA;
   }
   return check_launch("ua_modedota_sharded_step_f32");
+}
+
+extern "C" int ua_debug_sample_trace(int64_t* host_out16) {
+  return cudaMemcpyFromSymbol(host_out16, ua::g_sample_trace, sizeof(long long) * 16) == cudaSuccess ? UA_OK : UA_ERR_CUDA;
 }

@@ -275,17 +275,23 @@ class _FusedRank:
         self.flag = flag if flag is not None else torch.zeros(2 * P, dtype=torch.int32, device=dev)
         self.seq = torch.zeros(1, dtype=torch.int32, device=dev)
         self.err = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.done = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.done = torch.zeros(2, dtype=torch.int32, device=dev)
         self.c_sum = torch.full((1,), float(K), dtype=torch.float32, device=dev)     # initial soft counts sum to K
         self.out_final = torch.zeros(1, K, device=dev)
         self.out_argmax = torch.zeros(1, dtype=torch.int32, device=dev)
         self.out_clip = torch.zeros(1, K, device=dev)
         self.out_dota = torch.zeros(1, K, device=dev)
 
-    def struct(self, recv_ptrs, flag_ptrs):
+    def struct(self, recv_ptrs, flag_ptrs, in_kernel_head=True):
         from ._lib import ShardRank
         c = self.cache
-        return ShardRank(self.xn[0].data_ptr(), self.xn[1].data_ptr(), self.clip2.data_ptr(), c.mu.data_ptr(), c.var.data_ptr(),
+        if in_kernel_head:      # raw rows in, text rows in: the kernel normalises and forms the zero-shot logits itself
+            return ShardRank(self.x2[0].data_ptr(), self.x2[1].data_ptr(), self.text.data_ptr(), None, c.mu.data_ptr(),
+                             c.var.data_ptr(), c.pi.data_ptr(), c.c.data_ptr(), c.class_counts.data_ptr(), recv_ptrs.data_ptr(),
+                             flag_ptrs.data_ptr(), self.seq.data_ptr(), self.err.data_ptr(), self.done.data_ptr(),
+                             self.c_sum.data_ptr(), self.out_final.data_ptr(), self.out_argmax.data_ptr(),
+                             self.out_clip.data_ptr(), self.out_dota.data_ptr(), self.rank, 0)
+        return ShardRank(self.xn[0].data_ptr(), self.xn[1].data_ptr(), None, self.clip2.data_ptr(), c.mu.data_ptr(), c.var.data_ptr(),
                          c.pi.data_ptr(), c.c.data_ptr(), c.class_counts.data_ptr(), recv_ptrs.data_ptr(), flag_ptrs.data_ptr(),
                          self.seq.data_ptr(), self.err.data_ptr(), self.done.data_ptr(), self.c_sum.data_ptr(),
                          self.out_final.data_ptr(), self.out_argmax.data_ptr(), self.out_clip.data_ptr(),
@@ -305,7 +311,7 @@ class FusedShardedModeDota:
     ``emulate_only=r`` then launches rank r alone (its peers never arrive: the time-out path)."""
 
     def __init__(self, cfg, text, M, device, group=None, emulate_world: int | None = None, use_graph: bool = True,
-                 emulate_only: int | None = None):
+                 emulate_only: int | None = None, in_kernel_head: bool = True):
         from . import _lib
         import ctypes as C
         self.cfg, self.M = cfg, M
@@ -338,7 +344,10 @@ class FusedShardedModeDota:
             torch.cuda.synchronize()
             dist.barrier(group=group)      # every rank has zeroed its flags before anybody signals
         self.K_pad = self.ranks[0].K_pad
-        self._structs = (_lib.ShardRank * len(self.ranks))(*[r.struct(self._recv_ptrs, self._flag_ptrs) for r in self.ranks])
+        # True: ONE launch per step (normalisation and zero-shot logits inside the kernel); False: ua_head_f32 first
+        self.in_kernel_head = in_kernel_head
+        self._structs = (_lib.ShardRank * len(self.ranks))(*[r.struct(self._recv_ptrs, self._flag_ptrs, in_kernel_head)
+                                                              for r in self.ranks])
         self._structs_ptr = C.cast(self._structs, C.c_void_p)
 
     @property
@@ -348,7 +357,7 @@ class FusedShardedModeDota:
     def _launch(self):
         from . import _lib
         lib = _lib.lib()
-        for r in self.ranks:
+        for r in ([] if self.in_kernel_head else self.ranks):
             rc = lib.ua_head_f32(_lib.ptr(r.x2), 2, self.D, _lib.ptr(r.text), 1, r.Kp, 100.0, _lib.ptr(r.xn), _lib.ptr(r.clip2),
                                  None, None, None, _lib.stream_ptr())
             _lib.check(rc, "ua_head_f32")
