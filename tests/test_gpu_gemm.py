@@ -149,7 +149,9 @@ def test_tensor_core_head_vs_simt_head_and_golden(shape, cuda_device):
     text = torch.from_numpy(synth.unit_rows(K, D, 9)).to(cuda_device)
     x = torch.randn(B, D, generator=torch.Generator().manual_seed(B)).to(cuda_device)
     xn, logits, ent, prob, arg = HeadPlan(text)(x)
-    xn0, logits0, ent0, prob0, arg0 = ua.zero_shot_head(x, text)
+    xn0, logits0, ent0, prob0, arg0 = ua.zero_shot_head(x, text, tensor_cores=False)      # the SIMT kernels
+    xn1, logits1, ent1, prob1, arg1 = ua.zero_shot_head(x, text)                          # default: B >= 64 -> tcgen05
+    assert torch.equal(logits1, logits) and torch.equal(prob1, prob) and torch.equal(arg1, arg)
     assert torch.equal(xn, xn0)
     np.testing.assert_allclose(logits.cpu().numpy(), logits0.cpu().numpy(), rtol=1e-4, atol=5e-5)
     np.testing.assert_allclose(prob.cpu().numpy(), prob0.cpu().numpy(), rtol=2e-4, atol=1e-7)

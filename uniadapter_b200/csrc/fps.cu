@@ -28,16 +28,6 @@ namespace {
 
 constexpr float kFpsInit = 1e10f;
 
-// pointnet2_ops tie order. Upstream thread t = k mod bs owns point k and keeps its FIRST maximum; the pairwise tree
-// (t, t + bs/2), (t, t + bs/4), ... (0, 1) keeps the LEFT operand on ties, so among equal maxima the winner is the thread
-// with the smallest BIT-REVERSED id (the last level lets even threads beat odd ones, the one before decides bit 1, ...):
-// comp(k) = (bitrev_lg(k mod bs), k / bs) packed into one word with bs = 2^lg; ties go to the lowest comp.
-struct Pn2Order {
-  int lg, lq;      // bs = 2^lg; 2^lq >= ceil(N / bs): a power of two keeps the (thread, round) order and decodes by shifts
-  __device__ __forceinline__ uint32_t rev(uint32_t t) const { return lg ? (__brev(t) >> (32 - lg)) : 0u; }
-  __device__ __forceinline__ uint32_t comp(uint32_t k) const { return (rev(k & ((1u << lg) - 1u)) << lq) | (k >> lg); }
-  __device__ __forceinline__ uint32_t index(uint32_t c) const { return ((c & ((1u << lq) - 1u)) << lg) + rev(c >> lq); }
-};
 __device__ __forceinline__ float sqdist_pn2(float px, float py, float pz, float cx, float cy, float cz) {
   const float dx = __fsub_rn(px, cx), dy = __fsub_rn(py, cy), dz = __fsub_rn(pz, cz);
   return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
@@ -48,6 +38,16 @@ __device__ __forceinline__ bool pn2_skipped(float x, float y, float z) {
 // block / warp keys: 0 = no candidate (every owned point skipped), else distance bits + 1 (distances are >= 0)
 __device__ __forceinline__ uint32_t pn2_key(float best) { return best < 0.f ? 0u : __float_as_uint(best) + 1u; }
 
+// pointnet2_ops tie order. Upstream thread t = k mod bs owns point k and keeps its FIRST maximum; the pairwise tree
+// (t, t + bs/2), (t, t + bs/4), ... (0, 1) keeps the LEFT operand on ties, so among equal maxima the winner is the thread
+// with the smallest BIT-REVERSED id (the last level lets even threads beat odd ones, the one before decides bit 1, ...):
+// comp(k) = (bitrev_lg(k mod bs), k / bs) packed into one word with bs = 2^lg; ties go to the lowest comp.
+struct Pn2Order {
+  int lg, lq;      // bs = 2^lg; 2^lq >= ceil(N / bs): a power of two keeps the (thread, round) order and decodes by shifts
+  __device__ __forceinline__ uint32_t rev(uint32_t t) const { return lg ? (__brev(t) >> (32 - lg)) : 0u; }
+  __device__ __forceinline__ uint32_t comp(uint32_t k) const { return (rev(k & ((1u << lg) - 1u)) << lq) | (k >> lg); }
+  __device__ __forceinline__ uint32_t index(uint32_t c) const { return ((c & ((1u << lq) - 1u)) << lg) + rev(c >> lq); }
+};
 __device__ __forceinline__ void block_argmax(uint32_t bits, uint32_t idx, uint2 (*s_red)[32], int buf, int lane,
                                              int warp, int nwarps, uint32_t& out_idx) {
   // warp level: maximum of the (non-negative) float bit patterns, lowest index among the maxima
@@ -60,12 +60,14 @@ __device__ __forceinline__ void block_argmax(uint32_t bits, uint32_t idx, uint2 
   out_idx = __reduce_min_sync(kFullMask, v.x == bmax ? v.y : 0xffffffffu);
 }
 
-template <typename IdxT>
+// s_sel holds point indices -- or, in the pointnet2 mode, the tie-order words comp(k), which is also the position of
+// point k in the shared-memory copy of the cloud (no decode on the critical path of the sampling loop)
+template <typename IdxT, bool PN2 = false>
 __device__ __forceinline__ void write_selection(const int* s_sel, const float* cloud_smem, const float* cloud_gmem,
-                                                int b, int G, IdxT* out_idx, float* out_centers) {
+                                                int b, int G, IdxT* out_idx, float* out_centers, Pn2Order ord = Pn2Order()) {
   __syncthreads();
   for (int i = threadIdx.x; i < G; i += blockDim.x) {
-    const int p = s_sel[i];
+    const int p = PN2 ? (int)ord.index((uint32_t)s_sel[i]) : s_sel[i];
     if (out_idx) out_idx[(size_t)b * G + i] = (IdxT)p;
   }
   if (out_centers) {
@@ -85,8 +87,9 @@ __global__ void __launch_bounds__(PPT == 12 ? 896 : 1024, 1)
     fps_reg_kernel(const float* __restrict__ xyz, int N, int G, const long long* __restrict__ start_idx,
                    int skip_small, Pn2Order ord, IdxT* __restrict__ out_idx, float* __restrict__ out_centers) {
   extern __shared__ __align__(16) float s_dyn[];
-  float* s_xyz = s_dyn;                              // [3N]
-  int* s_sel = reinterpret_cast<int*>(s_dyn + 3 * N);  // [G]
+  const int slots = PN2 ? (1 << (ord.lg + ord.lq)) : N;
+  float* s_xyz = s_dyn;                              // [3 * slots]
+  int* s_sel = reinterpret_cast<int*>(s_dyn + 3 * slots);  // [G]
   __shared__ uint2 s_red[2][32];
 
   const int b = blockIdx.x;
@@ -95,17 +98,27 @@ __global__ void __launch_bounds__(PPT == 12 ? 896 : 1024, 1)
   const int lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
   const float* cloud = xyz + (size_t)b * N * 3;
 
-  for (int i = tid; i < 3 * N; i += T) s_xyz[i] = __ldg(cloud + i);
+  if (PN2) {   // the cloud sits in shared memory in tie order: point k at position comp(k)
+    for (int i = tid; i < 3 * N; i += T) {
+      const int k = i / 3;
+      s_xyz[3 * ord.comp((uint32_t)k) + (i - 3 * k)] = __ldg(cloud + i);
+    }
+  } else {
+    for (int i = tid; i < 3 * N; i += T) s_xyz[i] = __ldg(cloud + i);
+  }
   __syncthreads();
 
   float px[PPT], py[PPT], pz[PPT], dmin[PPT];
+  uint32_t cj[PN2 ? PPT : 1];
 #pragma unroll
   for (int j = 0; j < PPT; ++j) {
     const int p = j * T + tid;
     bool valid = p < N;
-    px[j] = valid ? s_xyz[3 * p + 0] : 0.f;
-    py[j] = valid ? s_xyz[3 * p + 1] : 0.f;
-    pz[j] = valid ? s_xyz[3 * p + 2] : 0.f;
+    const int pos = PN2 ? (int)ord.comp((uint32_t)p) : p;
+    if (PN2) cj[j] = (uint32_t)pos;
+    px[j] = valid ? s_xyz[3 * pos + 0] : 0.f;
+    py[j] = valid ? s_xyz[3 * pos + 1] : 0.f;
+    pz[j] = valid ? s_xyz[3 * pos + 2] : 0.f;
     if (PN2) {
       // a point that never takes part keeps the running "distance" -1 (fminf(-1, d) = -1 < any candidate)
       if (valid) valid = !pn2_skipped(px[j], py[j], pz[j]);
@@ -120,7 +133,7 @@ __global__ void __launch_bounds__(PPT == 12 ? 896 : 1024, 1)
   long long s0 = start_idx ? start_idx[b] : 0;
   if (s0 < 0) s0 = 0;
   if (s0 >= N) s0 = N - 1;
-  uint32_t cur = (uint32_t)s0;
+  uint32_t cur = PN2 ? ord.comp((uint32_t)s0) : (uint32_t)s0;      // PN2: `cur` is a tie-order word = shared-memory position
 
   for (int i = 0; i < G; ++i) {
     if (tid == 0) s_sel[i] = (int)cur;
@@ -128,29 +141,27 @@ __global__ void __launch_bounds__(PPT == 12 ? 896 : 1024, 1)
     const float cx = s_xyz[3 * cur + 0], cy = s_xyz[3 * cur + 1], cz = s_xyz[3 * cur + 2];
     float best = -1.f;
     if (PN2) {
-      int bestj = 0;
-      bool tie = false;
+      uint32_t bestc = 0u;
+      int ties = 0;
 #pragma unroll
       for (int j = 0; j < PPT; ++j) {
         const float d = sqdist_pn2(px[j], py[j], pz[j], cx, cy, cz);
         const float dm = fminf(dmin[j], d);
         dmin[j] = dm;
-        tie |= dm == best;
         if (dm > best) {
           best = dm;
-          bestj = j;
-          tie = false;
+          bestc = cj[j];
         }
       }
-      uint32_t bestc = best < 0.f ? 0u : ord.comp((uint32_t)(bestj * T + tid));
-      if (tie && best >= 0.f) {     // rare (no vote on the critical path): several of this thread's points share its maximum
+#pragma unroll
+      for (int j = 0; j < PPT; ++j) ties += dmin[j] == best;
+      if (ties > 1 && best >= 0.f) {     // rare (no vote on the critical path): several of this thread's points share its maximum
 #pragma unroll
         for (int j = 0; j < PPT; ++j)
-          if (dmin[j] == best && best >= 0.f) bestc = min(bestc, ord.comp((uint32_t)(j * T + tid)));
+          if (dmin[j] == best) bestc = min(bestc, cj[j]);
       }
-      uint32_t win;
-      block_argmax(pn2_key(best), bestc, s_red, i & 1, lane, warp, nwarps, win);
-      cur = ord.index(win);      // nobody has a candidate: every thread reports comp 0 = point 0, as upstream
+      block_argmax(pn2_key(best), best < 0.f ? 0u : bestc, s_red, i & 1, lane, warp, nwarps, cur);
+      // nobody has a candidate: every thread reports word 0 = point 0, as upstream
     } else {
       int bestj = 0;
 #pragma unroll
@@ -166,7 +177,7 @@ __global__ void __launch_bounds__(PPT == 12 ? 896 : 1024, 1)
       block_argmax(__float_as_uint(best), (uint32_t)(bestj * T + tid), s_red, i & 1, lane, warp, nwarps, cur);
     }
   }
-  write_selection<IdxT>(s_sel, s_xyz, nullptr, b, G, out_idx, out_centers);
+  write_selection<IdxT, PN2>(s_sel, s_xyz, nullptr, b, G, out_idx, out_centers, ord);
 }
 
 
@@ -195,8 +206,9 @@ __global__ void __launch_bounds__(512, 1)
   extern __shared__ __align__(16) float s_dyn[];
   cg::cluster_group cluster = cg::this_cluster();
   const int C = (int)gridDim.x, rank = (int)blockIdx.x, b = blockIdx.y;
-  float* s_xyz = s_dyn;                                          // [3N] the whole cloud
-  int* s_sel = reinterpret_cast<int*>(s_dyn + 3 * N);            // [G]
+  const int slots = PN2 ? (1 << (ord.lg + ord.lq)) : N;
+  float* s_xyz = s_dyn;                                          // [3 * slots] the whole cloud (PN2: in tie order)
+  int* s_sel = reinterpret_cast<int*>(s_dyn + 3 * slots);        // [G]
   __shared__ __align__(16) unsigned long long s_mine[2];         // [parity] this CTA's candidate, read by every peer
   __shared__ uint32_t s_cur[2];                                  // [parity] the cluster-wide winner, for the other warps
   __shared__ uint2 s_red[2][32];
@@ -207,17 +219,27 @@ __global__ void __launch_bounds__(512, 1)
   const int n0 = rank * chunk, nl = max(0, min(N, n0 + chunk) - n0);
 
   if (tid < 2) s_mine[tid] = 0ull;                               // tag 0 = nothing published yet
-  for (int i = tid; i < 3 * N; i += T) s_xyz[i] = __ldg(cloud + i);
+  if (PN2) {
+    for (int i = tid; i < 3 * N; i += T) {
+      const int k = i / 3;
+      s_xyz[3 * ord.comp((uint32_t)k) + (i - 3 * k)] = __ldg(cloud + i);
+    }
+  } else {
+    for (int i = tid; i < 3 * N; i += T) s_xyz[i] = __ldg(cloud + i);
+  }
   __syncthreads();
 
   float px[PPT], py[PPT], pz[PPT], dmin[PPT];
+  uint32_t cj[PN2 ? PPT : 1];
 #pragma unroll
   for (int j = 0; j < PPT; ++j) {
     const int p = j * T + tid;
     bool valid = p < nl;
-    px[j] = valid ? s_xyz[3 * (n0 + p) + 0] : 0.f;
-    py[j] = valid ? s_xyz[3 * (n0 + p) + 1] : 0.f;
-    pz[j] = valid ? s_xyz[3 * (n0 + p) + 2] : 0.f;
+    const int pos = PN2 ? (int)ord.comp((uint32_t)(n0 + (valid ? p : 0))) : n0 + p;
+    if (PN2) cj[j] = (uint32_t)pos;
+    px[j] = valid ? s_xyz[3 * pos + 0] : 0.f;
+    py[j] = valid ? s_xyz[3 * pos + 1] : 0.f;
+    pz[j] = valid ? s_xyz[3 * pos + 2] : 0.f;
     if (PN2) {
       if (valid) valid = !pn2_skipped(px[j], py[j], pz[j]);
       dmin[j] = valid ? kFpsInit : -1.f;
@@ -230,7 +252,7 @@ __global__ void __launch_bounds__(512, 1)
   long long s0 = start_idx ? start_idx[b] : 0;
   if (s0 < 0) s0 = 0;
   if (s0 >= N) s0 = N - 1;
-  uint32_t cur = (uint32_t)s0;
+  uint32_t cur = PN2 ? ord.comp((uint32_t)s0) : (uint32_t)s0;     // PN2: a tie-order word = shared-memory position
   uint32_t peer_slot = 0;          // lane r < C: cluster address of CTA r's slot (parity 0)
   if (lane < C)
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer_slot) : "r"(smem_u32(&s_mine[0])), "r"(lane));
@@ -243,26 +265,26 @@ __global__ void __launch_bounds__(512, 1)
     float best = -1.f;
     uint32_t bits, cand;           // this thread's candidate: key (distance bits) and tie-order word
     if (PN2) {
-      int bestj = 0;
-      bool tie = false;
+      uint32_t bestc = 0u;
+      int ties = 0;
 #pragma unroll
       for (int j = 0; j < PPT; ++j) {
         const float d = sqdist_pn2(px[j], py[j], pz[j], cx, cy, cz);
         const float dm = fminf(dmin[j], d);
         dmin[j] = dm;
-        tie |= dm == best;
         if (dm > best) {
           best = dm;
-          bestj = j;
-          tie = false;
+          bestc = cj[j];
         }
       }
-      uint32_t bestc = best < 0.f ? 0u : ord.comp((uint32_t)(n0 + bestj * T + tid));
-      if (tie && best >= 0.f) {     // rare (no vote on the critical path): several of this thread's points share its maximum
+#pragma unroll
+      for (int j = 0; j < PPT; ++j) ties += dmin[j] == best;
+      if (ties > 1 && best >= 0.f) {     // rare: several of this thread's points share its maximum
 #pragma unroll
         for (int j = 0; j < PPT; ++j)
-          if (dmin[j] == best && best >= 0.f) bestc = min(bestc, ord.comp((uint32_t)(n0 + j * T + tid)));
+          if (dmin[j] == best) bestc = min(bestc, cj[j]);
       }
+      if (best < 0.f) bestc = 0u;
       bits = pn2_key(best), cand = bestc;
     } else {
       int bestj = 0;
@@ -321,10 +343,10 @@ __global__ void __launch_bounds__(512, 1)
       if (lane == 0) s_cur[par] = g;
     }
     __syncthreads();
-    const uint32_t gidx = PN2 ? ord.index(s_cur[par]) : s_cur[par];
-    cur = gidx < (uint32_t)N ? gidx : 0u;     // (all slices empty cannot happen: N >= 1)
+    const uint32_t gidx = s_cur[par];
+    cur = PN2 ? gidx : (gidx < (uint32_t)N ? gidx : 0u);     // (all slices empty cannot happen: N >= 1)
   }
-  if (rank == 0) write_selection<IdxT>(s_sel, s_xyz, nullptr, b, G, out_idx, out_centers);   // every CTA holds the same list
+  if (rank == 0) write_selection<IdxT, PN2>(s_sel, s_xyz, nullptr, b, G, out_idx, out_centers, ord);   // every CTA holds the same list
   cluster.sync();
 }
 
@@ -375,7 +397,9 @@ __global__ void __launch_bounds__(1024, 1)
 template <int PPT, typename IdxT, bool PN2>
 int launch_reg(const float* xyz, int B, int N, int G, const int64_t* start_idx, int skip_small, Pn2Order ord,
                void* out_idx, float* out_centers, int threads, cudaStream_t st) {
-  const size_t smem = (size_t)3 * N * sizeof(float) + (size_t)G * sizeof(int);
+  const size_t slots = PN2 ? ((size_t)1 << (ord.lg + ord.lq)) : (size_t)N;     // tie-order positions are padded to a power of two
+  const size_t smem = (size_t)3 * slots * sizeof(float) + (size_t)G * sizeof(int);
+  UA_UNSUPPORTED(smem > 226 * 1024, "ua_fps_f32: N=%d does not fit in shared memory in the pointnet2 layout", N);
   auto kern = fps_reg_kernel<PPT, IdxT, PN2>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -416,7 +440,8 @@ int dispatch(const float* xyz, int B, int N, int G, const int64_t* start_idx, in
       const int chunk = (N + C - 1) / C;
       const int threads = (((chunk + kFpsClusterPpt - 1) / kFpsClusterPpt) + 31) / 32 * 32;
       if (threads <= 512) {
-        const size_t smem = (size_t)3 * N * sizeof(float) + (size_t)G * sizeof(int);
+        const size_t slots = PN2 ? ((size_t)1 << (ord.lg + ord.lq)) : (size_t)N;
+        const size_t smem = (size_t)3 * slots * sizeof(float) + (size_t)G * sizeof(int);
         auto kern = fps_cluster_kernel<IdxT, PN2>;
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaLaunchConfig_t cfg = {};

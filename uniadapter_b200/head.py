@@ -10,9 +10,18 @@ import torch
 from . import _lib
 
 
-def zero_shot_head(x: torch.Tensor, text: torch.Tensor, scale: float = 100.0, *, want_prob: bool = True):
+TENSOR_CORE_MIN_BATCH = 64      # rows from which the head is a dense contraction worth the tcgen05 GEMM (BASELINE cfg 5)
+
+
+def zero_shot_head(x: torch.Tensor, text: torch.Tensor, scale: float = 100.0, *, want_prob: bool = True,
+                   tensor_cores: bool | None = None):
     """x (B,D) raw encoder output, text (K,D) [or (S,K,D): one matrix per block of B/S rows]
-    -> (xnorm, logits, entropy, prob, argmax int32 (B,))."""
+    -> (xnorm, logits, entropy, prob, argmax int32 (B,)).
+
+    Batch 1 (the reference loop) is a GEMV that streams the text matrix once: SIMT kernels. From
+    ``TENSOR_CORE_MIN_BATCH`` rows on, with one shared text matrix and D % 32 == 0, the contraction runs on the tcgen05
+    3xTF32 GEMM (:class:`HeadPlan`; the text rows are split per call, so a text matrix that residual learning keeps
+    changing is always current). ``tensor_cores`` forces (True) or forbids (False) that path."""
     x = x.float().contiguous()
     text = text.float().contiguous()
     B, D = x.shape
@@ -20,6 +29,12 @@ def zero_shot_head(x: torch.Tensor, text: torch.Tensor, scale: float = 100.0, *,
     K = text.shape[-2]
     if text.shape[-1] != D:
         raise ValueError(f"text features {tuple(text.shape)} do not match feature dim {D}")
+    if tensor_cores is None:
+        tensor_cores = B >= TENSOR_CORE_MIN_BATCH and num_text == 1 and D % 32 == 0 and x.is_cuda
+    if tensor_cores:
+        if num_text != 1 or D % 32:
+            raise _lib.UaError("the tensor-core head needs one shared text matrix and D % 32 == 0")
+        return HeadPlan(text.reshape(K, D), scale)(x, want_prob=want_prob)
     dev = x.device
     xnorm = torch.empty_like(x)
     logits = torch.empty((B, K), dtype=torch.float32, device=dev)
