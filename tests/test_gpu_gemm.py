@@ -187,3 +187,28 @@ def test_tensor_core_attention_vs_sdpa_float64(shape, cuda_device):
     q, k, v = qkv.view(B, N, 3, H, 64).permute(2, 0, 3, 1, 4)
     ref = F.scaled_dot_product_attention(q.double(), k.double(), v.double()).transpose(1, 2).reshape(B * N, C)
     np.testing.assert_allclose((hi + lo).cpu().numpy(), ref.float().cpu().numpy(), rtol=2e-5, atol=1e-5)
+
+
+def test_tensor_core_plans_follow_load_state_dict(cuda_device):
+    """The tcgen05 plans snapshot (fold + split) the weights when they are attached; loading other weights must rebuild them
+    (a later load_state_dict used to be ignored silently)."""
+    from uniadapter_b200.encoders import UlipPointBert, use_tensor_cores
+    from uniadapter_b200.streams import unit_sphere_clouds
+    dev = cuda_device
+    torch.manual_seed(1)
+    a = use_tensor_cores(UlipPointBert(depth=1).to(dev).eval(), True)
+    torch.manual_seed(2)
+    donor = UlipPointBert(depth=1).to(dev).eval()
+    pc = unit_sphere_clouds(2, 1024, torch.Generator().manual_seed(3)).to(dev)
+    start = torch.zeros(2, dtype=torch.long, device=dev)
+
+    def run(m):
+        m.point_encoder.group_divider.next_start_idx = start
+        with torch.no_grad():
+            return m(pc)
+    before = run(a)
+    a.load_state_dict(donor.state_dict())
+    after = run(a)
+    want = run(use_tensor_cores(donor, True))
+    assert not torch.allclose(before, after, rtol=1e-3, atol=1e-3)
+    assert torch.equal(after, want)

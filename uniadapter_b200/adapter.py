@@ -105,6 +105,11 @@ def test_zeroshot_3d_core(test_loader, validate_dataset_name, model, clip_model,
             dota_logits = adapter.predict(x_pred)
             adapter.fit(pc_features, prob_map)
             adapter.update()
+            # The reference's DOTA-only branch stops here without ever fusing (final_logits is undefined at
+            # Uni_Adapter.py:409-412). The fusion line is the one the reference documents (dota_mixture.py:289-293), placed
+            # where Uni_Adapter.py places its MODE-DOTA fusion (:491, AFTER the fits): the weight therefore sees c including
+            # this sample, one sample later than the usage comment of dota_mixture.py would. The goldens
+            # (oracle.make_golden.dota_goldens / e2e) use the same placement.
             final_logits, _, _ = fuse_logits(clip_logits, dota_logits, adapter.c, dota_cfg['rho'], dota_cfg['eta'], B,
                                              'dota')
         else:

@@ -382,13 +382,17 @@ __global__ void __launch_bounds__(b1_max_threads(V, G), 1) modedota_b1_kernel(co
   float* s_tiles = reinterpret_cast<float*>(s_raw);                        // [NS][2][MD]
   float* s_part = s_tiles + (size_t)NS * 2 * MD;                           // [G][2][32 warps][4]
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_part + G * 2 * 32 * 4);  // [NS]
+  int* s_issued = reinterpret_cast<int*>(s_bar + 8);                       // [NS] highest class index armed per stage
 
   const int total = p.S * p.K;
   const int first = blockIdx.x, stride = gridDim.x;
   const int n_mine = first < total ? (total - first + stride - 1) / stride : 0;
 
   if (tid == 0) {
-    for (int i = 0; i < NS; ++i) mbar_init(&s_bar[i], 1);
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&s_bar[i], 1);
+      s_issued[i] = i < n_mine ? i : -1;
+    }
     fence_mbar_init();
   }
   __syncthreads();
@@ -434,6 +438,14 @@ __global__ void __launch_bounds__(b1_max_threads(V, G), 1) modedota_b1_kernel(co
     const float* xp_row = PRED ? p.x_pred + (size_t)s * D + d0 : nullptr;   // the sample (L1-resident)
     const float* xf_row = FIT ? p.x_fit + (size_t)s * D + d0 : nullptr;
 
+    // The ring is shared by the groups and an mbarrier parity only tells adjacent phases apart: a group may look at a
+    // stage only once the load of ITS class has been armed (by the group that drained the stage's previous class);
+    // otherwise a group two phases ahead would pass the parity test on the previous class's tile.
+    if (lane == 0) {
+      while (*reinterpret_cast<volatile int*>(&s_issued[stage]) < j) {
+      }
+    }
+    __syncwarp();
     mbar_wait(&s_bar[stage], parity);
 
     // ---- likelihood pass: log-determinant and Mahalanobis partial sums of this warp's chunk ----------------
@@ -490,7 +502,10 @@ __global__ void __launch_bounds__(b1_max_threads(V, G), 1) modedota_b1_kernel(co
     if (lane == 0) *reinterpret_cast<float4*>(part + warp * 4) = make_float4(accp, accf, ld, 0.f);
     if (G == 1) __syncthreads(); else group_barrier(1 + grp, gwarps * 32);
     // every warp of the group has pulled the stage into registers: re-arm it NS classes ahead
-    if (warp == 0 && lane == 0 && j + NS < n_mine) issue_load(j + NS);
+    if (warp == 0 && lane == 0 && j + NS < n_mine) {
+      issue_load(j + NS);
+      *reinterpret_cast<volatile int*>(&s_issued[stage]) = j + NS;
+    }
 
     // ---- responsibilities: every warp evaluates all M modes (lane = mode; lanes 8.. idle when M <= 8) ------
     float mp = 0.f, mf = 0.f, ldet = 0.f;
@@ -637,7 +652,7 @@ extern "C" int ua_modedota_step_f32(const float* x_pred, int Bp, const float* x_
         V = cand, groups = gtry;
       }
     }
-    const size_t small = (size_t)2 * 2 * 32 * 4 * sizeof(float) + 8 * sizeof(uint64_t);
+    const size_t small = (size_t)2 * 2 * 32 * 4 * sizeof(float) + 8 * sizeof(uint64_t) + 8 * sizeof(int);
     int ns = 0;
     for (int cand = 4; cand >= 2 && !ns; --cand)
       if ((size_t)cand * 2 * tile_bytes + small <= budget && (cand <= 3 || 4 * 2 * tile_bytes <= 100 * 1024)) ns = cand;

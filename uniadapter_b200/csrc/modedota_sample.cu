@@ -641,9 +641,20 @@ struct Plan {
 
 // widest lanes first for two groups (more ILP per thread, fewer warps per barrier), else the narrowest fit; the ring
 // depth is a multiple of the group count where it can be (a stage then always serves the same group)
-Plan make_plan(int M, int D, size_t extra_smem) {
+Plan make_plan(int M, int D, size_t extra_smem, long long items = 1 << 30) {
   static const int kV[] = {1, 2, 4, 5, 8, 10};
   Plan pl;
+  // few (stream, class) tiles per SM: nothing for a second warp group to overlap with; one group, moderately wide lanes
+  // (measured, tools/dbg/sample_sweep_cfg2.py: cfg 3 shape 30.7 -> 22.5 us, cfg 2 shape 33.5 -> 31.5 us)
+  if (!g_sample_v && !g_sample_g && items < 4 * kNumSMs) {
+    for (int i = 3; i >= 0 && !pl.V; --i) {
+      const int cand = kV[i];
+      if (D % (128 * cand)) continue;
+      const int thr = 32 * M * (D / (128 * cand));
+      if (thr < 256 || thr > s_max_threads(cand, 1) || thr > 1024) continue;
+      pl.V = cand, pl.G = 1, pl.threads = thr;
+    }
+  }
   for (int gtry = 2; gtry >= 1 && !pl.V; --gtry) {
     if (g_sample_g > 0 && gtry != g_sample_g) continue;
     for (int i = 5; i >= 0 && !pl.V; --i) {
@@ -724,7 +735,7 @@ extern "C" int ua_modedota_sample_step_f32(const float* x_fit, const float* x_fi
   UA_UNSUPPORTED(((uintptr_t)mu | (uintptr_t)var | (uintptr_t)x_fit | (uintptr_t)x_fit2) & 15,
                  "ua_modedota_sample_step_f32: pointers must be 16-byte aligned");
   UA_UNSUPPORTED((long long)S * K > 0x3fffffffLL, "ua_modedota_sample_step_f32: S*K too large");
-  const Plan pl = make_plan(M, D, (size_t)3 * D * sizeof(float) + 16);
+  const Plan pl = make_plan(M, D, (size_t)3 * D * sizeof(float) + 16, (long long)S * K);
   UA_UNSUPPORTED(!pl.V, "ua_modedota_sample_step_f32: no register tiling for M=%d D=%d", M, D);
   LaunchParams lp = {};
   RankParams& r = lp.r[0];

@@ -279,6 +279,12 @@ def use_tensor_cores(model: nn.Module, flag: bool = True, linears: bool = True) 
     nn.Linear layers whose shapes the GEMM supports (N % 128 == 0, K % 32 == 0). Inference only; weights are folded
     and split when this is called, so call it again after loading other weights."""
     from .gemm import BlockPlan, GroupEncoderPlan, LinearPlan
+    if flag and not getattr(model, '_tc_reload_hook', None):
+        # the plans snapshot (fold + split) the weights: rebuild them whenever other weights are loaded
+        def _rebuild(module, incompatible_keys):      # (a post hook must return None)
+            use_tensor_cores(module, True, linears)
+
+        model._tc_reload_hook = model.register_load_state_dict_post_hook(_rebuild)
     for mod in model.modules():
         if isinstance(mod, MiniPointNet):
             mod._tc_plan = GroupEncoderPlan(mod) if flag else None
