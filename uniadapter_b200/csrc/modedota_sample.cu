@@ -644,17 +644,6 @@ struct Plan {
 Plan make_plan(int M, int D, size_t extra_smem, long long items = 1 << 30) {
   static const int kV[] = {1, 2, 4, 5, 8, 10};
   Plan pl;
-  // few (stream, class) tiles per SM: nothing for a second warp group to overlap with; one group, moderately wide lanes
-  // (measured, tools/dbg/sample_sweep_cfg2.py: cfg 3 shape 30.7 -> 22.5 us, cfg 2 shape 33.5 -> 31.5 us)
-  if (!g_sample_v && !g_sample_g && items < 4 * kNumSMs) {
-    for (int i = 3; i >= 0 && !pl.V; --i) {
-      const int cand = kV[i];
-      if (D % (128 * cand)) continue;
-      const int thr = 32 * M * (D / (128 * cand));
-      if (thr < 256 || thr > s_max_threads(cand, 1) || thr > 1024) continue;
-      pl.V = cand, pl.G = 1, pl.threads = thr;
-    }
-  }
   for (int gtry = 2; gtry >= 1 && !pl.V; --gtry) {
     if (g_sample_g > 0 && gtry != g_sample_g) continue;
     for (int i = 5; i >= 0 && !pl.V; --i) {
@@ -668,6 +657,10 @@ Plan make_plan(int M, int D, size_t extra_smem, long long items = 1 << 30) {
     }
   }
   if (!pl.V) return pl;
+  // few (stream, class) tiles per SM: nothing for a second warp group to overlap with -> one group, SAME lane width (the
+  // lane width fixes the summation order over D, the group count does not: results stay bit-identical across tilings,
+  // ranks and the two-launch sequence). Measured (tools/dbg/sample_sweep_cfg2.py): cfg 3 shape 30.7 -> 26.6 us, cfg 2 33.5 -> 31.5 us.
+  if (!g_sample_g && pl.G == 2 && items < 4 * kNumSMs && pl.threads / 2 >= 128) pl.G = 1, pl.threads /= 2;
   const size_t tile_bytes = (size_t)M * D * sizeof(float);
   const size_t small = (size_t)pl.G * 3 * 32 * 4 * sizeof(float) + 8 * sizeof(uint64_t) + 8 * sizeof(int) + extra_smem + 128;
   const size_t budget = 226 * 1024;
@@ -769,7 +762,7 @@ extern "C" int ua_modedota_sharded_step_f32(const ua_shard_rank* ranks, int n_ra
              K_pad);
   UA_UNSUPPORTED(M > kMaxM || D % 128 != 0, "ua_modedota_sharded_step_f32: needs M <= %d and D %% 128 == 0 (M=%d D=%d)", kMaxM,
                  M, D);
-  const Plan pl = make_plan(M, D, (size_t)(K + 4 * D) * sizeof(float) + 16);
+  const Plan pl = make_plan(M, D, (size_t)(K + 4 * D) * sizeof(float) + 16, (long long)(K + P - 1) / P);
   UA_UNSUPPORTED(!pl.V || pl.threads < P, "ua_modedota_sharded_step_f32: no register tiling for M=%d D=%d K=%d", M, D, K);
   UA_UNSUPPORTED((size_t)K * sizeof(float) > (size_t)pl.NS * 2 * M * D * sizeof(float),
                  "ua_modedota_sharded_step_f32: K=%d too large for the fusion scratch", K);
