@@ -12,6 +12,8 @@ static std::atomic<int64_t> g_launches{0};
 extern int g_fps_threads;
 extern int g_dota_ksplit;
 extern int g_dota_staged;
+extern int g_dota_ka;
+extern int g_dota_pdl;
 extern int g_fps_cluster;
 extern int g_knn_warps;
 extern int g_knn_hist;
@@ -26,6 +28,7 @@ extern int g_modedota_batch;
 extern int g_p2p_timeout_ms;
 extern int g_sample_v;
 extern int g_sample_g;
+extern int g_sample_per;
 extern int g_sample_skip;
 extern int g_sample_trace_on;
 
@@ -59,6 +62,8 @@ extern "C" int ua_set_tuning(const char* key, int value) {
   if (!key) return UA_ERR_INVALID_ARG;
   if (!strcmp(key, "fps_threads")) { ua::g_fps_threads = value; return UA_OK; }
   if (!strcmp(key, "dota_staged")) { ua::g_dota_staged = value; return UA_OK; }
+  if (!strcmp(key, "dota_ka")) { ua::g_dota_ka = value; return UA_OK; }
+  if (!strcmp(key, "dota_pdl")) { ua::g_dota_pdl = value; return UA_OK; }
   if (!strcmp(key, "dota_ksplit")) { ua::g_dota_ksplit = value; return UA_OK; }
   if (!strcmp(key, "fps_cluster")) { ua::g_fps_cluster = value; return UA_OK; }
   if (!strcmp(key, "knn_warps")) { ua::g_knn_warps = value; return UA_OK; }
@@ -74,6 +79,7 @@ extern "C" int ua_set_tuning(const char* key, int value) {
   if (!strcmp(key, "sample_v")) { ua::g_sample_v = value; return UA_OK; }
   if (!strcmp(key, "sample_trace")) { ua::g_sample_trace_on = value; return UA_OK; }
   if (!strcmp(key, "sample_skip")) { ua::g_sample_skip = value; return UA_OK; }
+  if (!strcmp(key, "sample_per")) { ua::g_sample_per = value; return UA_OK; }
   if (!strcmp(key, "sample_g")) { ua::g_sample_g = value; return UA_OK; }
   if (!strcmp(key, "p2p_timeout_ms")) { ua::g_p2p_timeout_ms = value; return UA_OK; }
   ua::set_error("ua_set_tuning: unknown key '%s'", key);

@@ -14,6 +14,8 @@ namespace ua {
 
 int g_dota_ksplit = 0;   // tuning: class splits (cluster size) of the fit kernel, 0 = heuristic
 int g_dota_staged = 1;   // tuning: 0 disables the staged batch-1 kernel (dota_sigma_b1_kernel)
+int g_dota_ka = 0;       // tuning: Sigma loads in flight per thread of the staged kernel (8, 10, 20; 0 = heuristic)
+int g_dota_pdl = 1;      // tuning: 0 launches the mean kernel without programmatic dependent launch
 
 namespace {
 
@@ -129,6 +131,20 @@ __global__ void __launch_bounds__(256)
   float2* s_sc = reinterpret_cast<float2*>(s_wi + (size_t)K * kTileRows);   // [K]
   const int t = threadIdx.y * 32 + threadIdx.x;
   const int j0 = blockIdx.x * kTileCols, i0 = blockIdx.y * kTileRows;
+  // the mean kernel may be scheduled behind this grid right away (programmatic dependent launch): it blocks in
+  // griddepcontrol.wait until this grid has completed, so only its launch latency overlaps
+  asm volatile("griddepcontrol.launch_dependents;");
+  const int j = j0 + threadIdx.x * 4, i = i0 + threadIdx.y;
+  const bool inside = i < D && j < D;
+  const size_t DD = (size_t)D * D;
+  float* sp = Sigma + (size_t)(inside ? i : 0) * D + (inside ? j : 0);
+  // the first KA tiles of the Sigma stream do not depend on the staging below: they fly while it runs
+  float4 sg0[KA];
+  const bool pre = inside && K >= KA;
+  if (pre) {
+#pragma unroll
+    for (int u = 0; u < KA; ++u) sg0[u] = __ldcs(reinterpret_cast<const float4*>(sp + (size_t)u * DD));
+  }
   for (int idx = t; idx < K * kTileCols; idx += 256) {
     const int k = idx / kTileCols, col = idx - k * kTileCols, jj = j0 + col;
     s_dj[idx] = jj < D ? __fsub_rn(__ldg(x + jj), __ldg(mu + (size_t)k * D + jj)) : 0.f;
@@ -142,10 +158,7 @@ __global__ void __launch_bounds__(256)
     s_sc[k] = make_float2(ck, rcp_rn_normal(__fadd_rn(ck, __ldg(y + k))));
   }
   __syncthreads();
-  const int j = j0 + threadIdx.x * 4, i = i0 + threadIdx.y;
-  if (i >= D || j >= D) return;
-  const size_t DD = (size_t)D * D;
-  float* sp = Sigma + (size_t)i * D + j;
+  if (!inside) return;
   float4 mean = make_float4(0.f, 0.f, 0.f, 0.f);
   auto update_class = [&](int k, const float4 sg) {
     const float4 dj = *reinterpret_cast<const float4*>(s_dj + (size_t)k * kTileCols + threadIdx.x * 4);
@@ -159,7 +172,14 @@ __global__ void __launch_bounds__(256)
     __stcs(reinterpret_cast<float4*>(sp + (size_t)k * DD), out);
     mean.x += out.x, mean.y += out.y, mean.z += out.z, mean.w += out.w;
   };
+  // full batches of KA classes, every load of a batch in flight before the first is consumed; what is left runs as
+  // guarded batches of 8 (K = 15 ran as 8 + 7 single dependent loads before)
   int k = 0;
+  if (pre) {
+#pragma unroll
+    for (int u = 0; u < KA; ++u) update_class(u, sg0[u]);
+    k = KA;
+  }
   for (; k + KA <= K; k += KA) {
     float4 sg[KA];
 #pragma unroll
@@ -167,7 +187,19 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int u = 0; u < KA; ++u) update_class(k + u, sg[u]);
   }
-  for (; k < K; ++k) update_class(k, __ldcs(reinterpret_cast<const float4*>(sp + (size_t)k * DD)));
+  if constexpr (KA >= 16) {   // (the wide variant has no registers to spare for a batched tail)
+    for (; k < K; ++k) update_class(k, __ldcs(reinterpret_cast<const float4*>(sp + (size_t)k * DD)));
+  } else {
+    for (; k < K; k += 8) {
+      float4 sg[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (k + u < K) sg[u] = __ldcs(reinterpret_cast<const float4*>(sp + (size_t)(k + u) * DD));
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (k + u < K) update_class(k + u, sg[u]);
+    }
+  }
   const float kf = (float)K;
   *reinterpret_cast<float4*>(overall + (size_t)i * D + j) =
       make_float4(__fdiv_rn(mean.x, kf), __fdiv_rn(mean.y, kf), __fdiv_rn(mean.z, kf), __fdiv_rn(mean.w, kf));
@@ -180,6 +212,9 @@ __global__ void __launch_bounds__(256)
   const int k = blockIdx.x;
   float sw = __ldg(y + k);
   for (int b = 1; b < B; ++b) sw = __fadd_rn(sw, __ldg(y + (size_t)b * K + k));
+  // launched as a programmatic dependent of the Sigma kernel (which reads the OLD mu and c): everything above overlaps
+  // with it, mu and c are touched only once that grid has completed (a no-op for a plain launch)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const float ck = c[k];
   const float denom = __fadd_rn(sw, ck);
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
@@ -283,10 +318,15 @@ extern "C" int ua_dota_fit_f32(const float* x, const float* y, int B, float* mu,
   if (KS > K) KS = 1;
   dim3 grid((D + kTileCols - 1) / kTileCols, (D + kTileRows - 1) / kTileRows, KS), block(32, kTileRows);
   const size_t staged_smem = (size_t)K * (kTileCols + kTileRows + 2) * sizeof(float);
+  bool pdl = false;
   if (B == 1 && g_dota_staged && KS == 1 && staged_smem <= 96 * 1024) {
-    auto kern = dota_sigma_b1_kernel<8>;
+    // loads in flight per thread: 20 when there are that many classes (K = 40, D = 512: 27.7 -> 23.6 us against 8; two
+    // CTAs per SM still fit), else 8 (+ one guarded batch for the rest)
+    int ka = g_dota_ka > 0 ? g_dota_ka : (K >= 20 ? 20 : 8);
+    auto kern = ka >= 20 ? dota_sigma_b1_kernel<20> : dota_sigma_b1_kernel<8>;
     if (staged_smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged_smem);
     kern<<<dim3(grid.x, grid.y), block, staged_smem, st>>>(x, y, mu, c, Sigma, overall, K, D);
+    pdl = g_dota_pdl != 0;
   } else if (KS == 1) {
     dota_sigma_kernel<<<grid, block, 0, st>>>(x, y, B, mu, c, Sigma, overall, K, D);
   } else {
@@ -304,6 +344,16 @@ extern "C" int ua_dota_fit_f32(const float* x, const float* y, int B, float* mu,
   }
   int rc = check_launch("ua_dota_fit_f32(sigma)");
   if (rc != UA_OK) return rc;
+  if (pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(K), cfg.blockDim = dim3(256), cfg.dynamicSmemBytes = 0, cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, dota_mean_kernel, x, y, B, mu, c, K, D) == cudaSuccess) return check_launch("ua_dota_fit_f32(mean)");
+    (void)cudaGetLastError();   // fall through to the plain launch
+  }
   dota_mean_kernel<<<K, 256, 0, st>>>(x, y, B, mu, c, K, D);
   return check_launch("ua_dota_fit_f32(mean)");
 }

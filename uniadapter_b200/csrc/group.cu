@@ -18,7 +18,7 @@
 namespace ua {
 
 int g_knn_warps = 0;  // tuning override (0 = heuristic)
-int g_knn_hist = 0;   // tuning: -1 disables the histogram selection of the first tile (streaming filter only)
+int g_knn_hist = 0;   // tuning: -1 = streaming filter only, 2 = candidate-buffer histogram selection only (no register masks)
 
 namespace {
 
@@ -60,7 +60,9 @@ struct TilePipe {
     bulk_g2s(sm->xyz[st], cloud + (size_t)3 * t * kTilePoints, bytes, &sm->bar[st]);
   }
   // Makes tile t resident (coordinates + squared norms) for every thread of the CTA; returns its stage.
-  __device__ __forceinline__ int acquire(int t) {
+  // soa: also lay the coordinates out as three planes X | Y | Z in the OTHER stage's buffer (single-tile clouds only:
+  // that stage is never filled), which the register-mask kNN selection reads with 16-byte loads.
+  __device__ __forceinline__ int acquire(int t, bool soa = false) {
     const int st = t & 1;
     const int tp = tile_points(t);
     if (bulk) {
@@ -72,8 +74,17 @@ struct TilePipe {
       for (int i = threadIdx.x; i < 3 * tp; i += blockDim.x) sm->xyz[st][i] = __ldg(src + i);
       __syncthreads();
     }
-    for (int p = threadIdx.x; p < tp; p += blockDim.x)
-      sm->pn[st][p] = sqnorm_nofma(sm->xyz[st][3 * p], sm->xyz[st][3 * p + 1], sm->xyz[st][3 * p + 2]);
+    if (soa) {
+      float* pl = sm->xyz[st ^ 1];
+      for (int p = threadIdx.x; p < tp; p += blockDim.x) {
+        const float x = sm->xyz[st][3 * p], y = sm->xyz[st][3 * p + 1], z = sm->xyz[st][3 * p + 2];
+        pl[p] = x, pl[kTilePoints + p] = y, pl[2 * kTilePoints + p] = z;
+        sm->pn[st][p] = sqnorm_nofma(x, y, z);
+      }
+    } else {
+      for (int p = threadIdx.x; p < tp; p += blockDim.x)
+        sm->pn[st][p] = sqnorm_nofma(sm->xyz[st][3 * p], sm->xyz[st][3 * p + 1], sm->xyz[st][3 * p + 2]);
+    }
     __syncthreads();
     return st;
   }
@@ -291,6 +302,181 @@ __device__ __forceinline__ bool knn_first_tile_hist(const float* __restrict__ sx
   return true;
 }
 
+
+// ---- single-tile clouds: selection on register masks ---------------------------------------------------------------
+// For clouds of one tile (N <= 1024: the ULIP / Uni3D 1024-point shapes) the candidate buffer disappears. A lane owns the
+// points p = 128 q + 4 lane + j (q < 8, j < 4; bit b = 4 q + j of its masks), read from the coordinate planes with four
+// 16-byte shared-memory loads per four points; the six operations of the reference's expanded distance run as packed
+// f32x2 instructions (two points per instruction, each half rounded exactly like the scalar operation), and the 32
+// distances stay in registers as sign-folded integers (the integer order is the float order, -0 < +0).
+//   1. 256-bin histogram over the top bits of the distance (32 bins per octave, the 8 octaves below the farthest point;
+//      everything nearer falls into bin 0), warp scan -> the bin b* that holds the k-th smallest;
+//   2. one pass builds two masks per lane: "below b*" (all selected) and "in b*" (at most 32 points in the warp, else the
+//      caller falls back to the candidate-buffer path);
+//   3. the points of b* go one per lane, are ranked by (distance bits, index) with one shuffle round per candidate, and
+//      the first k - below of them set their bit in the owner's mask through shared memory;
+//   4. the positions in ascending point-index order come from the masks alone: per-q counts packed as bytes, two warp
+//      scans, and each lane stores the indices of its own set bits (k / 32 on average) -- no ballot per point anywhere.
+// Bit-identical to the other paths: bins only pre-partition, the exact (distance bits, index) order decides.
+__device__ __forceinline__ int float_to_skey(float f) {
+  const int b = __float_as_int(f);
+  return b ^ ((b >> 31) & 0x7fffffff);
+}
+constexpr int kBinShift = 18;   // 32 bins per octave of the squared distance
+
+template <bool FULL>
+__device__ __forceinline__ bool knn_single_tile_masks(const float* __restrict__ planes, const float* __restrict__ sp, int tp,
+                                                      float cx, float cy, float cz, float cn, int k, int lane,
+                                                      uint32_t* scratch, uint32_t* bidx, int* hist) {
+  const float* X = planes;
+  const float* Y = planes + kTilePoints;
+  const float* Z = planes + 2 * kTilePoints;
+  int key[32];
+  int kmax = INT_MIN;
+  {
+    const u64 cx2 = pack2(cx, cx), cy2 = pack2(cy, cy), cz2 = pack2(cz, cz), cn2 = pack2(cn, cn), m2 = pack2(-2.0f, -2.0f);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int p0 = 128 * q + 4 * lane;
+      const ulonglong2 x = *reinterpret_cast<const ulonglong2*>(X + p0);
+      const ulonglong2 y = *reinterpret_cast<const ulonglong2*>(Y + p0);
+      const ulonglong2 z = *reinterpret_cast<const ulonglong2*>(Z + p0);
+      const ulonglong2 n = *reinterpret_cast<const ulonglong2*>(sp + p0);
+      // ((-2 * fma(cz,pz, fma(cy,py, cx*px))) + |c|^2) + |p|^2, two points per instruction
+      const u64 da = add2(add2(mul2(m2, fma2(cz2, z.x, fma2(cy2, y.x, mul2(cx2, x.x)))), cn2), n.x);
+      const u64 db = add2(add2(mul2(m2, fma2(cz2, z.y, fma2(cy2, y.y, mul2(cx2, x.y)))), cn2), n.y);
+      key[4 * q + 0] = float_to_skey(__uint_as_float((uint32_t)da));
+      key[4 * q + 1] = float_to_skey(__uint_as_float((uint32_t)(da >> 32)));
+      key[4 * q + 2] = float_to_skey(__uint_as_float((uint32_t)db));
+      key[4 * q + 3] = float_to_skey(__uint_as_float((uint32_t)(db >> 32)));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (!FULL && p0 + j >= tp) key[4 * q + j] = INT_MAX;
+        else kmax = max(kmax, key[4 * q + j]);
+      }
+    }
+  }
+  kmax = __reduce_max_sync(kFullMask, kmax);
+  const int off = (max(kmax, 0) >> kBinShift) - 255;     // bin(key) = max((key >> 18) - off, 0) <= 255
+#pragma unroll
+  for (int j = 0; j < 8; ++j) hist[lane + 32 * j] = 0;
+  __syncwarp();
+  const uint32_t hist_s = smem_u32(hist);
+#pragma unroll
+  for (int b = 0; b < 32; ++b)
+    if (FULL || key[b] != INT_MAX) {
+      const int bin = max((key[b] >> kBinShift) - off, 0);
+      asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist_s + 4u * (uint32_t)bin) : "memory");
+    }
+  __syncwarp();
+  // warp scan over the 256 counters (8 per lane)
+  int h[8];
+  {
+    const int4 a = *reinterpret_cast<const int4*>(hist + 8 * lane), b = *reinterpret_cast<const int4*>(hist + 8 * lane + 4);
+    h[0] = a.x, h[1] = a.y, h[2] = a.z, h[3] = a.w, h[4] = b.x, h[5] = b.y, h[6] = b.z, h[7] = b.w;
+  }
+  int ssum = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) ssum += h[j];
+  int incl = ssum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(kFullMask, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const unsigned mb = __ballot_sync(kFullMask, incl >= k);      // tp >= k, so some lane crosses
+  const int L = __ffs(mb) - 1;
+  int bstar = 0, below = 0, nb = 0;                             // below = points in bins < b*, nb = points in b*
+  if (lane == L) {
+    int c = incl - ssum;
+    bool found = false;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (!found && c + h[j] >= k) bstar = 8 * lane + j, below = c, nb = h[j], found = true;
+      c += h[j];
+    }
+  }
+  bstar = __shfl_sync(kFullMask, bstar, L);
+  below = __shfl_sync(kFullMask, below, L);
+  nb = __shfl_sync(kFullMask, nb, L);
+  if (nb > 32) return false;
+  const int need = k - below;                                   // 1 .. nb
+  // key range of bin b*: [lo, hi); bin 0 is open below
+  const int lo = bstar == 0 ? INT_MIN : (bstar + off) * (1 << kBinShift);
+  const long long hi64 = (long long)(bstar + off + 1) * (1 << kBinShift);
+  const int hi = hi64 > (long long)INT_MAX ? INT_MAX : (int)hi64;
+  uint32_t m_below = 0, m_lt_hi = 0;
+#pragma unroll
+  for (int b = 0; b < 32; ++b) {
+    if (key[b] < lo) m_below |= 1u << b;
+    if (key[b] < hi) m_lt_hi |= 1u << b;
+  }
+  const uint32_t m_in = m_lt_hi & ~m_below;
+  // the points of b*, one per lane: slots from a warp scan of the per-lane counts
+  uint32_t* cand = scratch;          // [32] point indices
+  uint32_t* selw = scratch + 32;     // [32] bits the ranked candidates add to their owner's mask
+  {
+    const int cnt = __popc(m_in);
+    int pos = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(kFullMask, pos, o);
+      if (lane >= o) pos += t;
+    }
+    pos -= cnt;
+    selw[lane] = 0u;
+    for (uint32_t mm = m_in; mm; mm &= mm - 1) {
+      const int b = __ffs(mm) - 1;
+      cand[pos++] = (uint32_t)(128 * (b >> 2) + 4 * lane + (b & 3));
+    }
+  }
+  __syncwarp();
+  {
+    int ck = INT_MAX, ci = INT_MAX;
+    if (lane < nb) {
+      ci = (int)cand[lane];
+      ck = float_to_skey(expanded_sqdist(cx, cy, cz, cn, X[ci], Y[ci], Z[ci], sp[ci]));
+    }
+    int rank = 0;
+    for (int i = 0; i < nb; ++i) {
+      const int ok = __shfl_sync(kFullMask, ck, i), oi = __shfl_sync(kFullMask, ci, i);
+      rank += (ok < ck || (ok == ck && oi < ci)) ? 1 : 0;
+    }
+    if (lane < nb && rank < need) atomicOr(&selw[(ci >> 2) & 31], 1u << (((ci >> 7) << 2) | (ci & 3)));
+  }
+  __syncwarp();
+  const uint32_t m = m_below | selw[lane];                      // this lane's selected points; k bits in the warp
+  // positions in ascending point order (q, lane, j): per-q counts as packed bytes, scanned over the lanes
+  uint32_t nib = m - ((m >> 1) & 0x55555555u);
+  nib = (nib & 0x33333333u) + ((nib >> 2) & 0x33333333u);       // nibble q = number of selected points of row q
+  const uint32_t c_even = nib & 0x0f0f0f0fu, c_odd = (nib >> 4) & 0x0f0f0f0fu;   // byte a: q = 2a / 2a + 1
+  uint32_t s_even = c_even, s_odd = c_odd;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t te = __shfl_up_sync(kFullMask, s_even, o), to = __shfl_up_sync(kFullMask, s_odd, o);
+    if (lane >= o) s_even += te, s_odd += to;
+  }
+  const uint32_t t_even = __shfl_sync(kFullMask, s_even, 31), t_odd = __shfl_sync(kFullMask, s_odd, 31);
+  {
+    // sanity: exactly k selected (every byte sum stays below 256 because the total is k <= 128)
+    const uint32_t tot = t_even + t_odd;
+    const int total = (int)((tot & 0xff) + ((tot >> 8) & 0xff) + ((tot >> 16) & 0xff) + (tot >> 24));
+    if (total != k) return false;
+  }
+  const uint32_t pair = t_even + t_odd;
+  const uint32_t E = (pair << 8) + (pair << 16) + (pair << 24);         // byte a: selected points of rows < 2a
+  const uint32_t w_even = E + (s_even - c_even);                        // byte a: first position of this lane in row 2a
+  const uint32_t w_odd = E + t_even + (s_odd - c_odd);                  //                                   row 2a + 1
+  for (uint32_t mm = m; mm; mm &= mm - 1) {
+    const int b = __ffs(mm) - 1, q = b >> 2, sh = 8 * (q >> 1);
+    const uint32_t w = (q & 1) ? w_odd : w_even;
+    const int pos = (int)((w >> sh) & 0xffu) + __popc(m & ((1u << b) - 1u) & (0xfu << (4 * q)));
+    bidx[pos] = (uint32_t)(128 * q + 4 * lane + (b & 3));
+  }
+  __syncwarp();
+  return true;
+}
+
 template <int CAP, typename IdxT>
 __global__ void __launch_bounds__(256, 3)   // 80 registers: 3 CTAs per SM (4 = 64 registers spills and is slower: 52.6 vs 43.8 us)
     knn_group_kernel(const float* __restrict__ xyz, const float* __restrict__ rgb, const float* __restrict__ centers,
@@ -323,14 +509,24 @@ __global__ void __launch_bounds__(256, 3)   // 80 registers: 3 CTAs per SM (4 = 
 
   TilePipe pipe;
   pipe.init(tiles, cloud, N, use_bulk);
+  const bool masks = use_hist == 1 && pipe.ntiles == 1;   // register-mask selection (single-tile clouds)
+  bool from_planes = false;
   for (int t = 0; t < pipe.ntiles; ++t) {
-    const int st = pipe.acquire(t);
+    const int st = pipe.acquire(t, masks);
     if (active) {
       const float* sx = tiles->xyz[st];
       const float* sp = tiles->pn[st];
       const int tp = pipe.tile_points(t), t0 = t * kTilePoints;
       bool done = false;
-      if (t == 0 && use_hist) {
+      if (masks) {
+        int* hist = s_hist + warp * 256;
+        done = tp == kTilePoints
+                   ? knn_single_tile_masks<true>(tiles->xyz[st ^ 1], sp, tp, cx, cy, cz, cn, k, lane, bkey, bidx, hist)
+                   : knn_single_tile_masks<false>(tiles->xyz[st ^ 1], sp, tp, cx, cy, cz, cn, k, lane, bkey, bidx, hist);
+        if (done) count = k;
+        from_planes = done;
+      }
+      if (!done && t == 0 && use_hist) {
         int* hist = s_hist + warp * 256;
         const bool more = pipe.ntiles > 1;
         done = tp == kTilePoints
@@ -368,8 +564,15 @@ __global__ void __launch_bounds__(256, 3)   // 80 registers: 3 CTAs per SM (4 = 
   for (int j = lane; j < k; j += 32) {
     const uint32_t p = bidx[j];
     if (out_idx) out_idx[row0 + j] = (IdxT)p;
-    const float* src = cloud + (size_t)3 * p;
-    const float nx = __fsub_rn(__ldg(src), cx), ny = __fsub_rn(__ldg(src + 1), cy), nz = __fsub_rn(__ldg(src + 2), cz);
+    float px, py, pz;
+    if (from_planes) {   // the tile is still resident: coordinates from shared memory
+      const float* pl = tiles->xyz[1];
+      px = pl[p], py = pl[kTilePoints + p], pz = pl[2 * kTilePoints + p];
+    } else {
+      const float* src = cloud + (size_t)3 * p;
+      px = __ldg(src), py = __ldg(src + 1), pz = __ldg(src + 2);
+    }
+    const float nx = __fsub_rn(px, cx), ny = __fsub_rn(py, cy), nz = __fsub_rn(pz, cz);
     if (out_neigh) {
       float* o = out_neigh + (row0 + j) * 3;
       o[0] = nx, o[1] = ny, o[2] = nz;
@@ -489,7 +692,7 @@ int launch_knn(const float* xyz, const float* rgb, const float* centers, int B, 
     }
   }
   dim3 grid((G + W - 1) / W, B);
-  kern<<<grid, W * 32, smem, st>>>(xyz, rgb, centers, N, G, k, use_bulk, g_knn_hist >= 0 ? 1 : 0, (IdxT*)out_idx, out_neigh,
+  kern<<<grid, W * 32, smem, st>>>(xyz, rgb, centers, N, G, k, use_bulk, g_knn_hist < 0 ? 0 : (g_knn_hist == 2 ? 2 : 1), (IdxT*)out_idx, out_neigh,
                                    out_feat);
   return check_launch("ua_knn_group_f32");
 }

@@ -37,6 +37,7 @@ namespace ua {
 int g_p2p_timeout_ms = 2000;   // tuning: bound of every in-kernel wait for a peer
 int g_sample_v = 0;            // tuning override: float4s per lane (0 = heuristic)
 int g_sample_g = 0;            // tuning override: warp groups per CTA (0 = heuristic)
+int g_sample_per = 0;          // tuning: CTAs per SM of the unsharded launch (0 = what the occupancy calculator allows)
 int g_sample_skip = 0;         // diagnosis only: bit 0 skips the class loop, bit 1 the fusion (timing of the phases)
 
 // diagnosis: phase time stamps (globaltimer, ns) of rank 0's CTA 0 (slots 0-7) and of its last CTA (slots 8-15)
@@ -674,12 +675,26 @@ Plan make_plan(int M, int D, size_t extra_smem, long long items = 1 << 30) {
   return pl;
 }
 
+// grid.x == 0 asks for the persistent grid: one CTA per resident slot as the occupancy calculator sees it (the register
+// budget of the wide variants allows ONE 512-thread CTA per SM), capped by the number of (stream, class) tiles
 template <int V, int G>
 cudaError_t launch_vg(const LaunchParams& lp, dim3 grid, int threads, size_t smem, bool coop, cudaStream_t st) {
   auto kern = modedota_sample_kernel<V, G>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   if (!coop) {
+    if (grid.x == 0) {
+      int per_sm = 0;
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
+      if (e != cudaSuccess) return e;
+      if (per_sm < 1) per_sm = 1;
+      if (per_sm > 4) per_sm = 4;
+      if (g_sample_per > 0) per_sm = g_sample_per;
+      long long g = (long long)kNumSMs * per_sm;
+      const long long total = (long long)lp.S * lp.r[0].K;
+      if (g > total) g = total;
+      grid.x = (unsigned)g;
+    }
     kern<<<grid, threads, smem, st>>>(lp);
     return cudaSuccess;
   }
@@ -736,14 +751,7 @@ extern "C" int ua_modedota_sample_step_f32(const float* x_fit, const float* x_fi
   r.mu = mu, r.var = var, r.pi = pi, r.c = c, r.class_counts = class_counts, r.out_logits = out_logits;
   r.K = K, r.ldg = ldg, r.kg_off = k_gamma_offset, r.ldo = ldo, r.ko_off = k_out_offset;
   lp.S = S, lp.M = M, lp.D = D, lp.eps = eps, lp.stages = pl.NS, lp.want_pred = out_logits != nullptr;
-  int per = (int)((226 * 1024) / (pl.smem + 1024));
-  if (per > 2048 / pl.threads) per = 2048 / pl.threads;
-  if (per < 1) per = 1;
-  if (per > 4) per = 4;
-  long long g = (long long)kNumSMs * per;
-  const long long total = (long long)S * K;
-  if (g > total) g = total;
-  cudaError_t e = launch_plan(pl, lp, dim3((unsigned)g), false, (cudaStream_t)stream);
+  cudaError_t e = launch_plan(pl, lp, dim3(0u), false, (cudaStream_t)stream);
   if (e != cudaSuccess) {
     set_error("ua_modedota_sample_step_f32: launch setup failed (%zu B smem): %s", pl.smem, cudaGetErrorString(e));
     return UA_ERR_CUDA;
@@ -762,7 +770,10 @@ extern "C" int ua_modedota_sharded_step_f32(const ua_shard_rank* ranks, int n_ra
              K_pad);
   UA_UNSUPPORTED(M > kMaxM || D % 128 != 0, "ua_modedota_sharded_step_f32: needs M <= %d and D %% 128 == 0 (M=%d D=%d)", kMaxM,
                  M, D);
-  const Plan pl = make_plan(M, D, (size_t)(K + 4 * D) * sizeof(float) + 16, (long long)(K + P - 1) / P);
+  // the same (V, G) plan for every P: the in-kernel softmax and fusion reductions run over the CTA's threads, so the group
+  // count is part of the summation order there and the result must not depend on the partition (P = 1, 2, 4, 8 give the
+  // same bits, tests/test_gpu_adapters.py)
+  const Plan pl = make_plan(M, D, (size_t)(K + 4 * D) * sizeof(float) + 16);
   UA_UNSUPPORTED(!pl.V || pl.threads < P, "ua_modedota_sharded_step_f32: no register tiling for M=%d D=%d K=%d", M, D, K);
   UA_UNSUPPORTED((size_t)K * sizeof(float) > (size_t)pl.NS * 2 * M * D * sizeof(float),
                  "ua_modedota_sharded_step_f32: K=%d too large for the fusion scratch", K);
