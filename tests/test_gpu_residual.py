@@ -60,10 +60,12 @@ def _warm_state(K, M, D, S, dev, seed):
     return text, cache
 
 
-@pytest.mark.parametrize("shape", [(40, 8, 512, 3), (15, 8, 1280, 2), (55, 4, 256, 1)])
+@pytest.mark.parametrize("shape", [(40, 8, 512, 3), (15, 8, 1280, 2), (55, 4, 256, 1), (216, 8, 512, 1), (300, 4, 512, 1),
+                                   (130, 4, 256, 2)])
 def test_residual_learner_vs_torch_autograd_adam(shape, cuda_device):
     """Two consecutive learn() calls (2 x 10 Adam steps, bias corrections continue) against torch autograd of the
-    reference-shaped loss + torch.optim.Adam, stream by stream."""
+    reference-shaped loss + torch.optim.Adam, stream by stream. K = 216 (OmniObject3D) and K = 300 take the large-K
+    forms: likelihood matrix read from global memory / P in global scratch, column-chunked backward kernel."""
     from uniadapter_b200.residual import ResidualLearner, compute_text_alignment_loss
     K, M, D, S = shape
     dev = cuda_device
@@ -117,7 +119,8 @@ def test_residual_learner_vs_torch_autograd_adam(shape, cuda_device):
         loss_err = np.abs(losses[s].cpu().numpy() - l64[10:]).max()
         assert loss_err <= 3.0 * np.abs(l32[10:] - l64[10:]).max() + 1e-5, (loss_err, np.abs(l32 - l64).max())
         cos = (learner.text[s].double() * t64).sum(-1)
-        assert float(cos.min()) > 1 - 1e-5, float(cos.min())
+        cos32 = (t32.double() * t64).sum(-1)          # torch's own fp32 run against float64: the yardstick again
+        assert 1 - float(cos.min()) < max(1e-5, 3.0 * (1 - float(cos32.min()))), (float(cos.min()), float(cos32.min()))
 
 
 def test_residual_learner_refresh_only(cuda_device):

@@ -16,20 +16,22 @@ def cu(a, dev):
 
 
 def knn_both_paths(xyz, centers, k, rgb=None):
-    """knn_group through both selection paths of the kernel: histogram selection of the first 1024-point tile
-    (default) and the pure streaming filter (tuning knob knn_hist = -1). They must agree bit for bit."""
+    """knn_group through every selection path of the kernel: the default (register-mask selection for clouds of one
+    1024-point tile, candidate-buffer histogram selection of the first tile otherwise), the candidate-buffer histogram
+    path alone (tuning knob knn_hist = 2) and the pure streaming filter (knn_hist = -1). They must agree bit for bit."""
     import uniadapter_b200 as ua
     from uniadapter_b200 import _lib
     res = ua.knn_group(xyz, centers, k, rgb, want_idx=True)
-    _lib.set_tuning("knn_hist", -1)
-    try:
-        alt = ua.knn_group(xyz, centers, k, rgb, want_idx=True)
-    finally:
-        _lib.set_tuning("knn_hist", 0)
-    for a, b in zip(res, alt):
-        assert (a is None) == (b is None)
-        if a is not None:
-            assert torch.equal(a, b)
+    for mode in (2, -1):
+        _lib.set_tuning("knn_hist", mode)
+        try:
+            alt = ua.knn_group(xyz, centers, k, rgb, want_idx=True)
+        finally:
+            _lib.set_tuning("knn_hist", 0)
+        for a, b in zip(res, alt):
+            assert (a is None) == (b is None)
+            if a is not None:
+                assert torch.equal(a, b), f"selection path {mode} differs from the default path"
     return res
 
 
@@ -252,3 +254,30 @@ def test_fps_pointnet2_vs_torch_order_disagreement_on_cfg4_clouds(cuda_device):
     print(f"pointnet2 vs torch-order FPS, 8 clouds x 10 000 points, 512 samples: positions differing {pos.tolist()}, "
           f"samples not shared {sets}")
     assert (a[:, :16] == b[:, :16]).all() and max(sets) < 256
+
+
+@pytest.mark.parametrize("B,N,G,k,kind", [(3, 1024, 96, 64, "plain"), (2, 1024, 64, 128, "plain"), (2, 1024, 64, 1, "plain"),
+                                          (2, 1000, 50, 32, "plain"), (2, 516, 40, 8, "plain"), (1, 100, 10, 100, "plain"),
+                                          (2, 1024, 64, 32, "lattice"), (2, 1024, 64, 64, "halves"), (1, 1024, 32, 32, "tiny")])
+def test_knn_register_mask_selection_vs_oracle(B, N, G, k, kind, cuda_device):
+    """Single-tile clouds (N <= 1024) take the register-mask selection of csrc/group.cu (packed f32x2 distances, 256-bin
+    histogram, the bin of the k-th neighbour ranked one candidate per lane, positions from mask scans). Same index sets,
+    same ascending order and the same grouped tensors as the oracle, on ragged tiles, k = 1 and k = N, lattice clouds (exact
+    distance ties everywhere), duplicated halves and clouds scaled to 1e-4 (bins far below the unit sphere)."""
+    from oracle import synth
+    xyz_np = synth.cloud(B, N, 977 + N + k)
+    if kind == "lattice":
+        xyz_np = (np.round(xyz_np * 6) / 6).astype(np.float32)
+    if kind == "halves":
+        xyz_np[:, N // 2:] = xyz_np[:, : N - N // 2]
+    if kind == "tiny":
+        xyz_np = (xyz_np * np.float32(1e-4)).astype(np.float32)
+    rng = np.random.default_rng(N + k)
+    centers_np = np.ascontiguousarray(np.stack([xyz_np[b, rng.choice(N, G, replace=False)] for b in range(B)]))
+    rgb_np = rng.random((B, N, 3), dtype=np.float32)
+    kidx, neigh, feat = knn_both_paths(cu(xyz_np, cuda_device), cu(centers_np, cuda_device), k, cu(rgb_np, cuda_device))
+    o_idx = np.sort(T.knn(xyz_np, centers_np, k, threads=4), axis=-1)
+    np.testing.assert_array_equal(kidx.cpu().numpy(), o_idx)
+    rel = (T.gather(xyz_np, o_idx) - centers_np[:, :, None, :]).astype(np.float32)
+    np.testing.assert_array_equal(neigh.cpu().numpy(), rel)
+    np.testing.assert_array_equal(feat.cpu().numpy(), np.concatenate([rel, T.gather(rgb_np, o_idx)], -1))

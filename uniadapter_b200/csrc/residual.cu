@@ -237,26 +237,31 @@ __global__ void __launch_bounds__(kThreads, 3) resid_forward_kernel(const FwdPar
 }
 
 // ---- loss and its gradient w.r.t. the likelihood matrix; W <- dLM * softmax weights ----------------------------
+// WHERE = 0: LM and P = exp(exp(LM / max)) both in shared memory (K <= ~160); 1: P in shared memory, LM read from global
+// memory (L2) each time (K <= ~230); 2: P in a global scratch array as well (any K: one CTA per stream walks K*K elements,
+// which is small next to the K*K*M*D contraction of the forward / backward kernels around it).
+template <int WHERE>
 __global__ void __launch_bounds__(kThreads) resid_loss_kernel(const float* __restrict__ LM, float* __restrict__ Wt,
-                                                              int K, int M, float* __restrict__ out_loss,
-                                                              int loss_stride, int loss_index) {
+                                                              float* __restrict__ Pg, int K, int M,
+                                                              float* __restrict__ out_loss, int loss_stride, int loss_index) {
   extern __shared__ __align__(16) float s_l[];
-  float* s_lm = s_l;                 // [K*K]
-  float* s_p = s_lm + K * K;         // [K*K]
-  float* s_s1 = s_p + K * K;         // [K] row sums
-  float* s_s2 = s_s1 + K;            // [K] column sums
-  float* s_dg = s_s2 + K;            // [K] diagonal of P
-  __shared__ float s_tmp[8];
-  __shared__ float s_best[8];
-  __shared__ int s_besti[8];
   const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int KK = K * K;
   const float* lm = LM + (size_t)s * KK;
+  float* s_s1 = s_l;                 // [K] row sums
+  float* s_s2 = s_s1 + K;            // [K] column sums
+  float* s_dg = s_s2 + K;            // [K] diagonal of P
+  float* s_p = WHERE == 2 ? Pg + (size_t)s * KK : s_dg + K;          // [K*K]
+  float* s_lmw = WHERE == 0 ? s_dg + K + KK : nullptr;                // [K*K] (WHERE == 0 only)
+  const float* s_lm = WHERE == 0 ? s_lmw : lm;
+  __shared__ float s_tmp[8];
+  __shared__ float s_best[8];
+  __shared__ int s_besti[8];
   float best = -INFINITY;
   int besti = 0x7fffffff;
   for (int e = tid; e < KK; e += kThreads) {
     const float v = lm[e];
-    s_lm[e] = v;
+    if (WHERE == 0) s_lmw[e] = v;
     if (v > best) best = v, besti = e;   // ascending e per thread: keeps the first maximum
   }
   for (int o = 16; o > 0; o >>= 1) {
@@ -301,9 +306,10 @@ __global__ void __launch_bounds__(kThreads) resid_loss_kernel(const float* __res
     const float di = s_dg[i], dk = s_dg[k];
     float dP = (__fdiv_rn(di, s_s1[i] * s_s1[i]) + __fdiv_rn(dk, s_s2[k] * s_s2[k])) * invK;
     if (i == k) dP -= (__fdiv_rn(1.0f, s_s1[i]) + __fdiv_rn(1.0f, s_s2[i])) * invK;
-    const float q = expf(__fdiv_rn(s_lm[e], lmax));
+    const float lme = s_lm[e];
+    const float q = expf(__fdiv_rn(lme, lmax));
     const float dZ = dP * s_p[e] * q;
-    tot = fmaf(dZ, s_lm[e], tot);
+    tot = fmaf(dZ, lme, tot);
     s_p[e] = __fdiv_rn(dZ, lmax);   // dLM without the arg-max term
   }
   tot = block_sum_256(tot, s_tmp);
@@ -311,7 +317,7 @@ __global__ void __launch_bounds__(kThreads) resid_loss_kernel(const float* __res
   if (tid == 0) s_p[besti] -= __fdiv_rn(tot, lmax * lmax);   // gradient through max(): lands on the arg-max
   __syncthreads();
   float* w = Wt + (size_t)s * KK * M;
-  for (int e = tid; e < KK * M; e += kThreads) w[e] *= s_p[e / M];
+  for (size_t e = tid; e < (size_t)KK * M; e += kThreads) w[e] *= s_p[e / M];
 }
 
 // ---- backward: dX and the row dots of the normalisation backward ---------------------------------------------------
@@ -394,17 +400,96 @@ __global__ void __launch_bounds__(kThreads, DBL == 1 ? 2 : 1) resid_backward_ker
   }
 }
 
+// The same contraction when the K*M columns of a D slice do not fit in shared memory (K*M > 880: e.g. OmniObject3D's 216
+// classes): grid (D slices, row blocks, S). A warp owns ONE group of kBR rows for the whole launch, so its accumulators stay
+// in registers while the CTA walks the columns in chunks of CC, restaging mu and 1/v per chunk (from L2: the state of a
+// stream is a few MB). Same arithmetic and summation order over the columns as the kernel above.
+template <int DBL>
+__global__ void __launch_bounds__(kThreads, 2) resid_backward_chunked_kernel(const BwdParams p, int CC) {
+  extern __shared__ __align__(16) float s_b[];
+  constexpr int DB = 32 * DBL;
+  const int K = p.K, M = p.M, D = p.D, ncols = K * M;
+  const int s = blockIdx.z, dbase = blockIdx.x * DB;
+  float* t_mu = s_b;                         // [CC][DB]
+  float* t_iv = t_mu + (size_t)CC * DB;      // [CC][DB]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* gmu = p.mu + (size_t)s * ncols * D + dbase;
+  const float* gvar = p.var + (size_t)s * ncols * D + dbase;
+  const int rg = blockIdx.y * (kThreads / 32) + warp;
+  const bool have = rg * kBR < K;
+  int rowi[kBR];
+#pragma unroll
+  for (int r = 0; r < kBR; ++r) rowi[r] = min(rg * kBR + r, K - 1);
+  float x[kBR][DBL], acc[kBR][DBL];
+  const float* wrow[kBR];
+#pragma unroll
+  for (int r = 0; r < kBR; ++r) {
+    wrow[r] = p.Wt + ((size_t)s * K + rowi[r]) * ncols;
+#pragma unroll
+    for (int e = 0; e < DBL; ++e) {
+      x[r][e] = __ldg(p.X + ((size_t)s * K + rowi[r]) * D + dbase + lane * DBL + e);
+      acc[r][e] = 0.f;
+    }
+  }
+  for (int c0 = 0; c0 < ncols; c0 += CC) {
+    const int nc = min(CC, ncols - c0);       // a multiple of 4 (CC and K*M are)
+    __syncthreads();                          // the previous chunk has been consumed by every warp
+    for (int idx = tid; idx < nc * DB; idx += kThreads) {
+      const int col = idx / DB, d = idx - col * DB;
+      t_mu[idx] = __ldg(gmu + (size_t)(c0 + col) * D + d);
+      t_iv[idx] = __ldg(gvar + (size_t)(c0 + col) * D + d);
+    }
+    __syncthreads();
+    if (have) {
+      for (int c4 = 0; c4 < nc; c4 += 4) {
+        float4 w4[kBR];
+#pragma unroll
+        for (int r = 0; r < kBR; ++r) w4[r] = __ldg(reinterpret_cast<const float4*>(wrow[r] + c0 + c4));
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float mq[DBL], iq[DBL];
+#pragma unroll
+          for (int e = 0; e < DBL; ++e) {
+            mq[e] = t_mu[(size_t)(c4 + q) * DB + lane * DBL + e];
+            iq[e] = t_iv[(size_t)(c4 + q) * DB + lane * DBL + e];
+          }
+#pragma unroll
+          for (int r = 0; r < kBR; ++r) {
+            const float w = q == 0 ? w4[r].x : (q == 1 ? w4[r].y : (q == 2 ? w4[r].z : w4[r].w));
+#pragma unroll
+            for (int e = 0; e < DBL; ++e) acc[r][e] = fmaf(w, (x[r][e] - mq[e]) * iq[e], acc[r][e]);
+          }
+        }
+      }
+    }
+  }
+  if (!have) return;
+#pragma unroll
+  for (int r = 0; r < kBR; ++r) {
+    float dot = 0.f;
+#pragma unroll
+    for (int e = 0; e < DBL; ++e) {
+      const float dx = -acc[r][e];
+      dot = fmaf(x[r][e], dx, dot);
+      if (rg * kBR + r < K) p.dX[((size_t)s * K + rowi[r]) * D + dbase + lane * DBL + e] = dx;
+    }
+    dot = warp_sum(dot);
+    if (lane == 0 && rg * kBR + r < K) p.rdot[((size_t)s * K + rowi[r]) * p.NB + blockIdx.x] = dot;
+  }
+}
+
 struct Plan {
   int CB, nblk, DBL, NB;
+  int loss_where;      // resid_loss_kernel<WHERE>
+  int bwd_cc, bwd_rb;  // chunked backward: columns per chunk (0 = all columns resident), row blocks
   size_t smem_fwd, smem_loss, smem_bwd;
   // scratch offsets (floats)
-  size_t o_nrm, o_consts, o_lm, o_wt, o_dx, o_rdot, o_inv, total;
+  size_t o_nrm, o_consts, o_lm, o_wt, o_dx, o_rdot, o_inv, o_p, total;
 };
 
 int make_plan(int S, int K, int M, int D, Plan& pl) {
   UA_UNSUPPORTED(D % 128 != 0, "residual learning: D=%d must be a multiple of 128", D);
   UA_UNSUPPORTED(M % 4 != 0 || M > 16, "residual learning: M=%d must be 4, 8, 12 or 16", M);
-  UA_UNSUPPORTED(K > 128, "residual learning: K=%d > 128 (the likelihood matrix is kept in shared memory)", K);
   const size_t budget = 220 * 1024;
   // forward: CB classes per CTA, tiles 2*CB*M*D floats + lj K*CB*M floats. One class per CTA on purpose: several small
   // CTAs per SM hide latency far better than one fat CTA with eight warps (measured at S=15, K=40: 10 Adam steps take
@@ -419,18 +504,30 @@ int make_plan(int S, int K, int M, int D, Plan& pl) {
   pl.CB = cb;
   pl.nblk = (K + pl.CB - 1) / pl.CB;
   pl.smem_fwd = ((size_t)2 * pl.CB * M * D + (size_t)K * pl.CB * M) * sizeof(float);
-  pl.smem_loss = ((size_t)2 * K * K + 3 * K) * sizeof(float);
-  // backward: the D slice (32 or 64 wide) whose K*M columns fit; the narrow slice when that makes two CTAs resident
-  pl.DBL = 0;
+  UA_UNSUPPORTED(pl.smem_fwd > budget, "residual learning: K*M=%d rows of log-likelihoods do not fit next to the class tile", K * M);
+  // loss: LM and P in shared memory while they fit, then P only, then P in global scratch (one CTA per stream either way)
+  const size_t kk = (size_t)K * K * sizeof(float), k3 = (size_t)3 * K * sizeof(float);
+  UA_UNSUPPORTED(k3 > budget, "residual learning: K=%d too large", K);
+  pl.loss_where = 2 * kk + k3 <= budget ? 0 : (kk + k3 <= budget ? 1 : 2);
+  pl.smem_loss = k3 + (pl.loss_where == 0 ? 2 * kk : (pl.loss_where == 1 ? kk : 0));
+  // backward: the D slice (32 or 64 wide) whose K*M columns fit; the narrow slice when that makes two CTAs resident.
+  // When not even the narrow slice fits (K*M > 880), the chunked kernel: 400 columns per chunk, 40 rows per CTA.
+  pl.DBL = 0, pl.bwd_cc = 0, pl.bwd_rb = 1;
   for (int dbl = 2; dbl >= 1 && !pl.DBL; --dbl)
     if ((size_t)2 * K * M * 32 * dbl * sizeof(float) <= budget && D % (32 * dbl) == 0) pl.DBL = dbl;
-  UA_UNSUPPORTED(!pl.DBL, "residual learning: K*M=%d columns do not fit in shared memory", K * M);
-  if (pl.DBL == 2 && (size_t)2 * K * M * 32 * sizeof(float) <= budget / 2) pl.DBL = 1;   // two CTAs resident per SM
-  if (g_resid_dbl == 1 || g_resid_dbl == 2) {
-    if ((size_t)2 * K * M * 32 * g_resid_dbl * sizeof(float) <= budget && D % (32 * g_resid_dbl) == 0) pl.DBL = g_resid_dbl;
+  if (!pl.DBL) {
+    pl.DBL = 1;
+    pl.bwd_cc = 400;
+    pl.bwd_rb = ((K + kBR - 1) / kBR + kThreads / 32 - 1) / (kThreads / 32);
+    UA_UNSUPPORTED(pl.bwd_rb > 65535, "residual learning: K=%d too large", K);
+  } else {
+    if (pl.DBL == 2 && (size_t)2 * K * M * 32 * sizeof(float) <= budget / 2) pl.DBL = 1;   // two CTAs resident per SM
+    if (g_resid_dbl == 1 || g_resid_dbl == 2) {
+      if ((size_t)2 * K * M * 32 * g_resid_dbl * sizeof(float) <= budget && D % (32 * g_resid_dbl) == 0) pl.DBL = g_resid_dbl;
+    }
   }
   pl.NB = D / (32 * pl.DBL);
-  pl.smem_bwd = (size_t)2 * K * M * 32 * pl.DBL * sizeof(float);
+  pl.smem_bwd = (size_t)2 * (pl.bwd_cc ? pl.bwd_cc : K * M) * 32 * pl.DBL * sizeof(float);
   return UA_OK;
 }
 
@@ -447,6 +544,7 @@ int plan_aligned(int S, int K, int M, int D, Plan& pl) {
   pl.o_dx = o, o = align4(o + (size_t)S * K * D);
   pl.o_rdot = o, o = align4(o + (size_t)S * K * pl.NB);
   pl.o_inv = o, o = align4(o + (size_t)S * K * M * D);
+  pl.o_p = o, o = align4(o + (pl.loss_where == 2 ? (size_t)S * K * K : 0));
   pl.total = o;
   return UA_OK;
 }
@@ -494,18 +592,35 @@ int launch_fwd_loss_bwd(const Run& r, float* out_loss, int loss_stride, int loss
   resid_forward_kernel<<<dim3(r.pl.nblk, r.S), kThreads, r.pl.smem_fwd, r.st>>>(fp);
   int rc = check_launch("resid_forward");
   if (rc != UA_OK) return rc;
-  if (opt_in(resid_loss_kernel, r.pl.smem_loss) != cudaSuccess) {
-    set_error("residual learning: cannot opt in to %zu B of shared memory (loss)", r.pl.smem_loss);
-    return UA_ERR_CUDA;
+  {
+    float* pg = r.scratch + r.pl.o_p;
+    cudaError_t e;
+    if (r.pl.loss_where == 0) {
+      e = opt_in(resid_loss_kernel<0>, r.pl.smem_loss);
+      if (e == cudaSuccess) resid_loss_kernel<0><<<r.S, kThreads, r.pl.smem_loss, r.st>>>(fp.LM, fp.Wt, pg, r.K, r.M, out_loss, loss_stride, loss_index);
+    } else if (r.pl.loss_where == 1) {
+      e = opt_in(resid_loss_kernel<1>, r.pl.smem_loss);
+      if (e == cudaSuccess) resid_loss_kernel<1><<<r.S, kThreads, r.pl.smem_loss, r.st>>>(fp.LM, fp.Wt, pg, r.K, r.M, out_loss, loss_stride, loss_index);
+    } else {
+      e = opt_in(resid_loss_kernel<2>, r.pl.smem_loss);
+      if (e == cudaSuccess) resid_loss_kernel<2><<<r.S, kThreads, r.pl.smem_loss, r.st>>>(fp.LM, fp.Wt, pg, r.K, r.M, out_loss, loss_stride, loss_index);
+    }
+    if (e != cudaSuccess) {
+      set_error("residual learning: cannot opt in to %zu B of shared memory (loss)", r.pl.smem_loss);
+      return UA_ERR_CUDA;
+    }
   }
-  resid_loss_kernel<<<r.S, kThreads, r.pl.smem_loss, r.st>>>(fp.LM, fp.Wt, r.K, r.M, out_loss, loss_stride, loss_index);
   rc = check_launch("resid_loss");
   if (rc != UA_OK || !backward) return rc;
   BwdParams bp;
   bp.X = r.X, bp.mu = r.mu, bp.var = r.scratch + r.pl.o_inv, bp.Wt = fp.Wt, bp.dX = r.scratch + r.pl.o_dx;
   bp.rdot = r.scratch + r.pl.o_rdot, bp.K = r.K, bp.M = r.M, bp.D = r.D, bp.NB = r.pl.NB, bp.eps = r.eps;
   cudaError_t e;
-  if (r.pl.DBL == 2) {
+  if (r.pl.bwd_cc) {
+    e = opt_in(resid_backward_chunked_kernel<1>, r.pl.smem_bwd);
+    if (e == cudaSuccess)
+      resid_backward_chunked_kernel<1><<<dim3(r.pl.NB, r.pl.bwd_rb, r.S), kThreads, r.pl.smem_bwd, r.st>>>(bp, r.pl.bwd_cc);
+  } else if (r.pl.DBL == 2) {
     e = opt_in(resid_backward_kernel<2>, r.pl.smem_bwd);
     if (e == cudaSuccess) resid_backward_kernel<2><<<dim3(r.pl.NB, r.S), kThreads, r.pl.smem_bwd, r.st>>>(bp);
   } else {
