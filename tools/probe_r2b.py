@@ -48,6 +48,7 @@ if "knn" in what:
             idx, neigh, feat = ua.knn_group(xyz, centers, k, rgb, want_idx=True)
             torch.cuda.synchronize()
             outs[mode] = (idx, neigh, feat)
+        _lib.set_tuning("knn_hist", 0)
         ok = all(torch.equal(outs[0][i], outs[-1][i]) for i in range(3) if outs[0][i] is not None)
         ok2 = all(torch.equal(outs[2][i], outs[-1][i]) for i in range(3) if outs[2][i] is not None)
         print(f"  B={B} N={N} G={G} k={k} colour={col} {kind}: masks == streaming: {ok}; histogram == streaming: {ok2}", flush=True)
@@ -58,15 +59,12 @@ if "knn" in what:
         rgb = torch.rand(B, N, 3, generator=g).to(dev)
         _, centers = ua.fps_sample(xyz, G, None)
         row = []
-        for mode in (0, 2):
-            for w in (0, 4, 8):
-                if B < 64 and w == 8:
-                    continue
-                _lib.set_tuning("knn_hist", mode)
-                _lib.set_tuning("knn_warps", w)
-                t64 = med(lambda: ua.knn_group(xyz, centers, 64, rgb))
-                t32 = med(lambda: ua.knn_group(xyz, centers, 32))
-                row.append(f"hist={mode} W={w}: k64+rgb {t64:7.1f} k32 {t32:7.1f}")
+        for mode, w in ((0, 0), (2, 0), (-1, 0)):
+            _lib.set_tuning("knn_hist", mode)
+            _lib.set_tuning("knn_warps", w)
+            t64 = med(lambda: ua.knn_group(xyz, centers, 64, rgb))
+            t32 = med(lambda: ua.knn_group(xyz, centers, 32))
+            row.append(f"hist={mode} W={w}: k64+rgb {t64:7.1f} k32 {t32:7.1f}")
         _lib.set_tuning("knn_hist", 0)
         _lib.set_tuning("knn_warps", 0)
         f = med(lambda: ua.fps_sample(xyz, G, None))

@@ -67,5 +67,12 @@ xb = torch.nn.functional.normalize(torch.randn(Bb, D, device=dev), dim=-1)
 gb = torch.softmax(100 * xb @ tb.t(), 1)
 for _ in range(ROUNDS):
     cold(); mb.predict_then_fit(xb, xb, gb)
+# cfg 5 zero-shot head at batch 64 on the tcgen05 GEMM (HeadPlan: prepare + 3xTF32 GEMM + row statistics), K = 55 and 1156
+xh = torch.randn(64, D, device=dev)
+for Kh in (55, 1156):
+    th = torch.from_numpy(synth.unit_rows(Kh, D, Kh)).to(dev)
+    ua.zero_shot_head(xh, th)
+    for _ in range(ROUNDS):
+        cold(); ua.zero_shot_head(xh, th)
 torch.cuda.synchronize()
 print("ok")
