@@ -210,8 +210,10 @@ def hbm_roofline(kernel, workload, alg_bytes, us, peak, peak_src, traffic_key=No
 # ----------------------------------------------------------------------------------------------------------------
 def cache_step_roofline(dev, flush, S, K, M, D, label):
     """The MODE-DOTA cache pass of a batch-1 sample step (predict + fit + fit on the jittered view) at a given state
-    shape: the single-pass kernel (each class tile read and written once: 16*S*K*M*D algorithmic bytes) beside the
-    two-launch sequence it replaces (predict+fit, fit: 32*S*K*M*D) and a plain device copy of the state bytes."""
+    shape: the single-pass kernel (each class tile read and written once: it MOVES 16*S*K*M*D bytes) beside the
+    two-launch sequence it replaces (predict+fit, fit: 32*S*K*M*D moved = SURVEY 8d's algorithmic bytes of a sample step)
+    and a plain device copy of the state bytes. `achieved` follows the contract (SURVEY 8d's per-unit figure x the units
+    one launch processes / the launch's duration); the conservative fraction over the bytes actually moved rides along."""
     from uniadapter_b200.engine import MultiStreamModeDota
     from uniadapter_b200.streams import synthetic_text_features
     peak, src = measured_peaks()
@@ -230,18 +232,27 @@ def cache_step_roofline(dev, flush, S, K, M, D, label):
         cache.step(None, xa.unsqueeze(1), g.unsqueeze(1))
     both = median_us(two, flush)
     one = median_us(lambda: cache.step(xp, x.unsqueeze(1), g.unsqueeze(1), out3), flush)
-    by = 16 * S * K * M * D
+    by = 16 * S * K * M * D                 # bytes the single pass has to move: every class tile in and out once
+    unit = 32 * S * K * M * D               # SURVEY 8d's per-unit figure: one sample step = two fits, state in + out per fit
     src_t = torch.empty(by // 8, device=dev)
     dst_t = torch.empty_like(src_t)
     copy_us = median_us(lambda: dst_t.copy_(src_t), flush)
-    return hbm_roofline("ua_modedota_sample_step_f32 (modedota_sample_kernel): predict + fit + fit, one pass", label, by,
-                        single, peak, src, traffic_key="modedota_sample_kernel_lvis" if K >= 1000 else None,
-                        two_launch_sequence_us=round(both, 2), two_launch_algorithmic_bytes=2 * by,
-                        two_launch_achieved_gbs=round(2 * by / both / 1e3, 1),
-                        predict_plus_one_fit_us=round(one, 2),
-                        predict_plus_one_fit_frac=round(by / one / 1e3 / peak, 4),
-                        predict_plus_one_fit_traffic=ncu_traffic("modedota_b1_kernel_lvis") if K >= 1000 else None,
-                        plain_copy_same_bytes_us=round(copy_us, 2), frac_of_plain_copy=round(copy_us / single, 4))
+    r = hbm_roofline("ua_modedota_sample_step_f32 (modedota_sample_kernel): predict + fit + fit, one pass", label, unit,
+                     single, peak, src, traffic_key="modedota_sample_kernel_lvis" if K >= 1000 else None,
+                     accounting="achieved / frac: SURVEY 8d's algorithmic bytes of a sample step (32*S*K*M*D: predict fused "
+                                "into fit #1, two fits, state in + out per fit) over the time of the ONE launch that does the "
+                                "whole sample step; the single pass moves half of them (moved_bytes_per_launch), the fraction "
+                                "over those bytes is frac_of_moved_bytes",
+                     moved_bytes_per_launch=by, achieved_over_moved_bytes=round(by / single / 1e3, 1),
+                     frac_of_moved_bytes=round(by / single / 1e3 / peak, 4),
+                     two_launch_sequence_us=round(both, 2), two_launch_algorithmic_bytes=2 * by,
+                     two_launch_achieved_gbs=round(2 * by / both / 1e3, 1),
+                     two_launch_frac=round(2 * by / both / 1e3 / peak, 4),
+                     predict_plus_one_fit_us=round(one, 2),
+                     predict_plus_one_fit_frac=round(by / one / 1e3 / peak, 4),
+                     predict_plus_one_fit_traffic=ncu_traffic("modedota_b1_kernel_lvis") if K >= 1000 else None,
+                     plain_copy_same_bytes_us=round(copy_us, 2), frac_of_plain_copy=round(copy_us / single, 4))
+    return r
 
 
 def tokenizer_roofline(dev, flush, B=64, N=1024, G=512, k=64, colored=True, sweep=(64, 148, 592, 1184)):

@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(kThreads) resid_loss_kernel(const float* __res
   if (tid == 0) s_p[besti] -= __fdiv_rn(tot, lmax * lmax);   // gradient through max(): lands on the arg-max
   __syncthreads();
   float* w = Wt + (size_t)s * KK * M;
-  for (size_t e = tid; e < (size_t)KK * M; e += kThreads) w[e] *= s_p[e / M];
+  for (int e = tid; e < KK * M; e += kThreads) w[e] *= s_p[e / M];   // (K*K*M < 2^31 is checked on the host: 32-bit division)
 }
 
 // ---- backward: dX and the row dots of the normalisation backward ---------------------------------------------------
@@ -507,7 +507,7 @@ int make_plan(int S, int K, int M, int D, Plan& pl) {
   UA_UNSUPPORTED(pl.smem_fwd > budget, "residual learning: K*M=%d rows of log-likelihoods do not fit next to the class tile", K * M);
   // loss: LM and P in shared memory while they fit, then P only, then P in global scratch (one CTA per stream either way)
   const size_t kk = (size_t)K * K * sizeof(float), k3 = (size_t)3 * K * sizeof(float);
-  UA_UNSUPPORTED(k3 > budget, "residual learning: K=%d too large", K);
+  UA_UNSUPPORTED(k3 > budget || (long long)K * K * M >= (1LL << 31), "residual learning: K=%d too large", K);
   pl.loss_where = 2 * kk + k3 <= budget ? 0 : (kk + k3 <= budget ? 1 : 2);
   pl.smem_loss = k3 + (pl.loss_where == 0 ? 2 * kk : (pl.loss_where == 1 ? kk : 0));
   // backward: the D slice (32 or 64 wide) whose K*M columns fit; the narrow slice when that makes two CTAs resident.
