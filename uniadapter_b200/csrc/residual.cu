@@ -31,6 +31,7 @@ constexpr int kRI = 5;    // rows per register tile (forward)
 constexpr int kCJ = 4;    // columns per register tile (forward)
 constexpr int kBR = 5;    // rows per register tile (backward)
 constexpr int kThreads = 256;
+constexpr int kLossThreads = 1024;
 
 __device__ __forceinline__ float block_sum_256(float v, float* s_tmp) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
@@ -241,7 +242,7 @@ __global__ void __launch_bounds__(kThreads, 3) resid_forward_kernel(const FwdPar
 // memory (L2) each time (K <= ~230); 2: P in a global scratch array as well (any K: one CTA per stream walks K*K elements,
 // which is small next to the K*K*M*D contraction of the forward / backward kernels around it).
 template <int WHERE>
-__global__ void __launch_bounds__(kThreads) resid_loss_kernel(const float* __restrict__ LM, float* __restrict__ Wt,
+__global__ void __launch_bounds__(kLossThreads) resid_loss_kernel(const float* __restrict__ LM, float* __restrict__ Wt,
                                                               float* __restrict__ Pg, int K, int M,
                                                               float* __restrict__ out_loss, int loss_stride, int loss_index) {
   extern __shared__ __align__(16) float s_l[];
@@ -254,12 +255,13 @@ __global__ void __launch_bounds__(kThreads) resid_loss_kernel(const float* __res
   float* s_p = WHERE == 2 ? Pg + (size_t)s * KK : s_dg + K;          // [K*K]
   float* s_lmw = WHERE == 0 ? s_dg + K + KK : nullptr;                // [K*K] (WHERE == 0 only)
   const float* s_lm = WHERE == 0 ? s_lmw : lm;
-  __shared__ float s_tmp[8];
-  __shared__ float s_best[8];
-  __shared__ int s_besti[8];
+  __shared__ float s_tmp[32];
+  __shared__ float s_best[32];
+  __shared__ int s_besti[32];
+  constexpr int kT = kLossThreads;   // one CTA per stream walks K*K elements in a chain of dependent phases: 1024 threads
   float best = -INFINITY;
   int besti = 0x7fffffff;
-  for (int e = tid; e < KK; e += kThreads) {
+  for (int e = tid; e < KK; e += kT) {
     const float v = lm[e];
     if (WHERE == 0) s_lmw[e] = v;
     if (v > best) best = v, besti = e;   // ascending e per thread: keeps the first maximum
@@ -272,18 +274,18 @@ __global__ void __launch_bounds__(kThreads) resid_loss_kernel(const float* __res
   if (lane == 0) s_best[warp] = best, s_besti[warp] = besti;
   __syncthreads();
   best = s_best[0], besti = s_besti[0];
-  for (int w = 1; w < kThreads / 32; ++w)
+  for (int w = 1; w < kT / 32; ++w)
     if (s_best[w] > best || (s_best[w] == best && s_besti[w] < besti)) best = s_best[w], besti = s_besti[w];
   const float lmax = best;
-  for (int e = tid; e < KK; e += kThreads) s_p[e] = expf(expf(__fdiv_rn(s_lm[e], lmax)));
+  for (int e = tid; e < KK; e += kT) s_p[e] = expf(expf(__fdiv_rn(s_lm[e], lmax)));
   __syncthreads();
-  for (int i = warp; i < K; i += kThreads / 32) {   // row sums
+  for (int i = warp; i < K; i += kT / 32) {   // row sums
     float t = 0.f;
     for (int k = lane; k < K; k += 32) t += s_p[i * K + k];
     t = warp_sum(t);
     if (lane == 0) s_s1[i] = t;
   }
-  for (int k = tid; k < K; k += kThreads) {         // column sums, diagonal
+  for (int k = tid; k < K; k += kT) {         // column sums, diagonal
     float t = 0.f;
     for (int i = 0; i < K; ++i) t += s_p[i * K + k];
     s_s2[k] = t;
@@ -293,7 +295,7 @@ __global__ void __launch_bounds__(kThreads) resid_loss_kernel(const float* __res
   const float invK = __fdiv_rn(1.0f, (float)K);
   if (out_loss) {
     float t = 0.f;
-    for (int i = tid; i < K; i += kThreads) {
+    for (int i = tid; i < K; i += kT) {
       t += __fdiv_rn(s_dg[i], s_s1[i]) + __fdiv_rn(s_dg[i], s_s2[i]);
     }
     t = block_sum_256(t, s_tmp);
@@ -301,7 +303,7 @@ __global__ void __launch_bounds__(kThreads) resid_loss_kernel(const float* __res
   }
   // dP[i,k] = (diag_i / s1_i^2 + diag_k / s2_k^2) / K  -  [i == k] (1/s1_i + 1/s2_i) / K
   float tot = 0.f;
-  for (int e = tid; e < KK; e += kThreads) {
+  for (int e = tid; e < KK; e += kT) {
     const int i = e / K, k = e - i * K;
     const float di = s_dg[i], dk = s_dg[k];
     float dP = (__fdiv_rn(di, s_s1[i] * s_s1[i]) + __fdiv_rn(dk, s_s2[k] * s_s2[k])) * invK;
@@ -317,7 +319,7 @@ __global__ void __launch_bounds__(kThreads) resid_loss_kernel(const float* __res
   if (tid == 0) s_p[besti] -= __fdiv_rn(tot, lmax * lmax);   // gradient through max(): lands on the arg-max
   __syncthreads();
   float* w = Wt + (size_t)s * KK * M;
-  for (int e = tid; e < KK * M; e += kThreads) w[e] *= s_p[e / M];   // (K*K*M < 2^31 is checked on the host: 32-bit division)
+  for (int e = tid; e < KK * M; e += kT) w[e] *= s_p[e / M];   // (K*K*M < 2^31 is checked on the host: 32-bit division)
 }
 
 // ---- backward: dX and the row dots of the normalisation backward ---------------------------------------------------
@@ -597,13 +599,13 @@ int launch_fwd_loss_bwd(const Run& r, float* out_loss, int loss_stride, int loss
     cudaError_t e;
     if (r.pl.loss_where == 0) {
       e = opt_in(resid_loss_kernel<0>, r.pl.smem_loss);
-      if (e == cudaSuccess) resid_loss_kernel<0><<<r.S, kThreads, r.pl.smem_loss, r.st>>>(fp.LM, fp.Wt, pg, r.K, r.M, out_loss, loss_stride, loss_index);
+      if (e == cudaSuccess) resid_loss_kernel<0><<<r.S, kLossThreads, r.pl.smem_loss, r.st>>>(fp.LM, fp.Wt, pg, r.K, r.M, out_loss, loss_stride, loss_index);
     } else if (r.pl.loss_where == 1) {
       e = opt_in(resid_loss_kernel<1>, r.pl.smem_loss);
-      if (e == cudaSuccess) resid_loss_kernel<1><<<r.S, kThreads, r.pl.smem_loss, r.st>>>(fp.LM, fp.Wt, pg, r.K, r.M, out_loss, loss_stride, loss_index);
+      if (e == cudaSuccess) resid_loss_kernel<1><<<r.S, kLossThreads, r.pl.smem_loss, r.st>>>(fp.LM, fp.Wt, pg, r.K, r.M, out_loss, loss_stride, loss_index);
     } else {
       e = opt_in(resid_loss_kernel<2>, r.pl.smem_loss);
-      if (e == cudaSuccess) resid_loss_kernel<2><<<r.S, kThreads, r.pl.smem_loss, r.st>>>(fp.LM, fp.Wt, pg, r.K, r.M, out_loss, loss_stride, loss_index);
+      if (e == cudaSuccess) resid_loss_kernel<2><<<r.S, kLossThreads, r.pl.smem_loss, r.st>>>(fp.LM, fp.Wt, pg, r.K, r.M, out_loss, loss_stride, loss_index);
     }
     if (e != cudaSuccess) {
       set_error("residual learning: cannot opt in to %zu B of shared memory (loss)", r.pl.smem_loss);
