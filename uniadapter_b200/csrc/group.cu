@@ -342,7 +342,9 @@ __device__ __forceinline__ bool knn_single_tile_masks(const float* __restrict__ 
       const ulonglong2 y = *reinterpret_cast<const ulonglong2*>(Y + p0);
       const ulonglong2 z = *reinterpret_cast<const ulonglong2*>(Z + p0);
       const ulonglong2 n = *reinterpret_cast<const ulonglong2*>(sp + p0);
-      // ((-2 * fma(cz,pz, fma(cy,py, cx*px))) + |c|^2) + |p|^2, two points per instruction
+      // ((-2 * fma(cz,pz, fma(cy,py, cx*px))) + |c|^2) + |p|^2, two points per instruction. ptxas contracts a
+      // mul.rn.f32x2 feeding an add.rn.f32x2 into one FFMA2 (tools/ubench/f32x2_contract.cu) -- here that pair is
+      // (-2 * dot) + |c|^2, and a multiplication by -2 is exact, so the contraction cannot change a bit
       const u64 da = add2(add2(mul2(m2, fma2(cz2, z.x, fma2(cy2, y.x, mul2(cx2, x.x)))), cn2), n.x);
       const u64 db = add2(add2(mul2(m2, fma2(cz2, z.y, fma2(cy2, y.y, mul2(cx2, x.y)))), cn2), n.y);
       key[4 * q + 0] = float_to_skey(__uint_as_float((uint32_t)da));
