@@ -308,7 +308,7 @@ __device__ __forceinline__ bool knn_first_tile_hist(const float* __restrict__ sx
 // points p = 128 q + 4 lane + j (q < 8, j < 4; bit b = 4 q + j of its masks), read from the coordinate planes with four
 // 16-byte shared-memory loads per four points; the six operations of the reference's expanded distance run as packed
 // f32x2 instructions (two points per instruction, each half rounded exactly like the scalar operation), and the 32
-// distances stay in registers as sign-folded integers (the integer order is the float order, -0 < +0).
+// distances stay in registers as 16 packed pairs.
 //   1. 256-bin histogram over the top bits of the distance (32 bins per octave, the 8 octaves below the farthest point;
 //      everything nearer falls into bin 0), warp scan -> the bin b* that holds the k-th smallest;
 //   2. one pass builds two masks per lane: "below b*" (all selected) and "in b*" (at most 32 points in the warp, else the
@@ -331,8 +331,9 @@ __device__ __forceinline__ bool knn_single_tile_masks(const float* __restrict__ 
   const float* X = planes;
   const float* Y = planes + kTilePoints;
   const float* Z = planes + 2 * kTilePoints;
-  int key[32];
-  int kmax = INT_MIN;
+  u64 dp[16];                   // the 32 distances as packed pairs: dp[2q] = points 4q, 4q+1; dp[2q+1] = points 4q+2, 4q+3
+  int kmax = INT_MIN;           // maximum of the float bit patterns as signed ints (>= 0 unless every distance is negative)
+  uint32_t vm = 0xffffffffu;    // this lane's points that exist (ragged tiles)
   {
     const u64 cx2 = pack2(cx, cx), cy2 = pack2(cy, cy), cz2 = pack2(cz, cz), cn2 = pack2(cn, cn), m2 = pack2(-2.0f, -2.0f);
 #pragma unroll
@@ -345,29 +346,31 @@ __device__ __forceinline__ bool knn_single_tile_masks(const float* __restrict__ 
       // ((-2 * fma(cz,pz, fma(cy,py, cx*px))) + |c|^2) + |p|^2, two points per instruction. ptxas contracts a
       // mul.rn.f32x2 feeding an add.rn.f32x2 into one FFMA2 (tools/ubench/f32x2_contract.cu) -- here that pair is
       // (-2 * dot) + |c|^2, and a multiplication by -2 is exact, so the contraction cannot change a bit
-      const u64 da = add2(add2(mul2(m2, fma2(cz2, z.x, fma2(cy2, y.x, mul2(cx2, x.x)))), cn2), n.x);
-      const u64 db = add2(add2(mul2(m2, fma2(cz2, z.y, fma2(cy2, y.y, mul2(cx2, x.y)))), cn2), n.y);
-      key[4 * q + 0] = float_to_skey(__uint_as_float((uint32_t)da));
-      key[4 * q + 1] = float_to_skey(__uint_as_float((uint32_t)(da >> 32)));
-      key[4 * q + 2] = float_to_skey(__uint_as_float((uint32_t)db));
-      key[4 * q + 3] = float_to_skey(__uint_as_float((uint32_t)(db >> 32)));
+      dp[2 * q] = add2(add2(mul2(m2, fma2(cz2, z.x, fma2(cy2, y.x, mul2(cx2, x.x)))), cn2), n.x);
+      dp[2 * q + 1] = add2(add2(mul2(m2, fma2(cz2, z.y, fma2(cy2, y.y, mul2(cx2, x.y)))), cn2), n.y);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        if (!FULL && p0 + j >= tp) key[4 * q + j] = INT_MAX;
-        else kmax = max(kmax, key[4 * q + j]);
+        const int bits = (int)(uint32_t)(dp[2 * q + (j >> 1)] >> (32 * (j & 1)));
+        if (!FULL && p0 + j >= tp) vm &= ~(1u << (4 * q + j));
+        else kmax = max(kmax, bits);
       }
     }
   }
+  // The distances stay floats: for d >= 0 the bit pattern is monotone, and the (rare, tiny) negative values of the expanded
+  // form all fall into bin 0 / below every threshold, so histogram and masks need no order-preserving integer image; only
+  // the <= 32 candidates of the k-th neighbour's bin are ranked on exact (sign-folded bits, index) pairs further down.
   kmax = __reduce_max_sync(kFullMask, kmax);
-  const int off = (max(kmax, 0) >> kBinShift) - 255;     // bin(key) = max((key >> 18) - off, 0) <= 255
+  const int off = (max(kmax, 0) >> kBinShift) - 255;     // bin(d) = max((bits(d) >> 18) - off, 0) <= 255
+  if (off < 0) return false;                             // farthest point nearer than 2^-119: leave it to the general path
 #pragma unroll
   for (int j = 0; j < 8; ++j) hist[lane + 32 * j] = 0;
   __syncwarp();
   const uint32_t hist_s = smem_u32(hist);
 #pragma unroll
   for (int b = 0; b < 32; ++b)
-    if (FULL || key[b] != INT_MAX) {
-      const int bin = max((key[b] >> kBinShift) - off, 0);
+    if (FULL || ((vm >> b) & 1u)) {
+      const int bits = (int)(uint32_t)(dp[b >> 1] >> (32 * (b & 1)));
+      const int bin = max((bits >> kBinShift) - off, 0);
       asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist_s + 4u * (uint32_t)bin) : "memory");
     }
   __syncwarp();
@@ -377,41 +380,49 @@ __device__ __forceinline__ bool knn_single_tile_masks(const float* __restrict__ 
     const int4 a = *reinterpret_cast<const int4*>(hist + 8 * lane), b = *reinterpret_cast<const int4*>(hist + 8 * lane + 4);
     h[0] = a.x, h[1] = a.y, h[2] = a.z, h[3] = a.w, h[4] = b.x, h[5] = b.y, h[6] = b.z, h[7] = b.w;
   }
-  int ssum = 0;
+  int pre[8];                                                   // inclusive prefix of this lane's 8 bins (lane-local)
+  pre[0] = h[0];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) ssum += h[j];
-  int incl = ssum;
+  for (int j = 1; j < 8; ++j) pre[j] = pre[j - 1] + h[j];
+  int incl = pre[7];
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const int t = __shfl_up_sync(kFullMask, incl, o);
     if (lane >= o) incl += t;
   }
+  const int excl = incl - pre[7];
   const unsigned mb = __ballot_sync(kFullMask, incl >= k);      // tp >= k, so some lane crosses
   const int L = __ffs(mb) - 1;
-  int bstar = 0, below = 0, nb = 0;                             // below = points in bins < b*, nb = points in b*
-  if (lane == L) {
-    int c = incl - ssum;
-    bool found = false;
+  // in lane L: the first bin whose inclusive prefix reaches k (branch-free: every lane evaluates its own 8 bins)
+  int jstar = 0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (!found && c + h[j] >= k) bstar = 8 * lane + j, below = c, nb = h[j], found = true;
-      c += h[j];
-    }
-  }
-  bstar = __shfl_sync(kFullMask, bstar, L);
-  below = __shfl_sync(kFullMask, below, L);
-  nb = __shfl_sync(kFullMask, nb, L);
+  for (int j = 0; j < 8; ++j) jstar += (excl + pre[j] < k) ? 1 : 0;
+  int nb_l = h[0], below_l = excl;
+#pragma unroll
+  for (int j = 1; j < 8; ++j)
+    if (jstar >= j) nb_l = h[j], below_l = excl + pre[j - 1];
+  const int bstar = 8 * L + __shfl_sync(kFullMask, jstar, L);  // the bin of the k-th neighbour
+  const int below = __shfl_sync(kFullMask, below_l, L);         // points in bins < b*
+  const int nb = __shfl_sync(kFullMask, nb_l, L);               // points in b*
   if (nb > 32) return false;
   const int need = k - below;                                   // 1 .. nb
-  // key range of bin b*: [lo, hi); bin 0 is open below
-  const int lo = bstar == 0 ? INT_MIN : (bstar + off) * (1 << kBinShift);
-  const long long hi64 = (long long)(bstar + off + 1) * (1 << kBinShift);
-  const int hi = hi64 > (long long)INT_MAX ? INT_MAX : (int)hi64;
+  // d-range of bin b*: [lo, hi) (bin 0 is open below). d < t  <=>  sign(d - t): one packed add per two points and one
+  // funnel shift per point and mask (the first point inserted ends up in bit 31: pairs are walked from the top)
+  const float lo_f = bstar == 0 ? -INFINITY : __int_as_float((bstar + off) << kBinShift);
+  const int hib = (bstar + off + 1) << kBinShift;               // <= 0x7f800000
+  const float hi_f = hib >= 0x7f800000 ? 3.402823466e38f : __int_as_float(hib);
   uint32_t m_below = 0, m_lt_hi = 0;
+  {
+    const u64 nlo2 = pack2(-lo_f, -lo_f), nhi2 = pack2(-hi_f, -hi_f);
 #pragma unroll
-  for (int b = 0; b < 32; ++b) {
-    if (key[b] < lo) m_below |= 1u << b;
-    if (key[b] < hi) m_lt_hi |= 1u << b;
+    for (int i = 15; i >= 0; --i) {
+      const u64 tl = add2(dp[i], nlo2), th = add2(dp[i], nhi2);
+      m_below = __funnelshift_l((uint32_t)(tl >> 32), m_below, 1);
+      m_below = __funnelshift_l((uint32_t)tl, m_below, 1);
+      m_lt_hi = __funnelshift_l((uint32_t)(th >> 32), m_lt_hi, 1);
+      m_lt_hi = __funnelshift_l((uint32_t)th, m_lt_hi, 1);
+    }
+    if (!FULL) m_below &= vm, m_lt_hi &= vm;
   }
   const uint32_t m_in = m_lt_hi & ~m_below;
   // the points of b*, one per lane: slots from a warp scan of the per-lane counts
@@ -469,11 +480,17 @@ __device__ __forceinline__ bool knn_single_tile_masks(const float* __restrict__ 
   const uint32_t E = (pair << 8) + (pair << 16) + (pair << 24);         // byte a: selected points of rows < 2a
   const uint32_t w_even = E + (s_even - c_even);                        // byte a: first position of this lane in row 2a
   const uint32_t w_odd = E + t_even + (s_odd - c_odd);                  //                                   row 2a + 1
-  for (uint32_t mm = m; mm; mm &= mm - 1) {
-    const int b = __ffs(mm) - 1, q = b >> 2, sh = 8 * (q >> 1);
-    const uint32_t w = (q & 1) ? w_odd : w_even;
-    const int pos = (int)((w >> sh) & 0xffu) + __popc(m & ((1u << b) - 1u) & (0xfu << (4 * q)));
-    bidx[pos] = (uint32_t)(128 * q + 4 * lane + (b & 3));
+  {
+    int prevq = -1, run = 0;                                            // selected points of this lane seen in the current row
+    const uint32_t lane4 = 4u * (uint32_t)lane;
+    for (uint32_t mm = m; mm; mm &= mm - 1) {
+      const int b = __ffs(mm) - 1, q = b >> 2;
+      run = q == prevq ? run + 1 : 0;
+      prevq = q;
+      const uint32_t w = (b & 4) ? w_odd : w_even;
+      const int pos = (int)__byte_perm(w, 0u, 0x4440u + (uint32_t)(b >> 3)) + run;   // byte q/2 of w + rank inside the row
+      bidx[pos] = ((uint32_t)q << 7) + lane4 + (uint32_t)(b & 3);
+    }
   }
   __syncwarp();
   return true;
