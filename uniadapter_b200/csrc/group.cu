@@ -516,18 +516,19 @@ __global__ void __launch_bounds__(256, 3)   // 80 registers: 3 CTAs per SM (4 = 
   uint32_t* bkey = s_key + (size_t)warp * CAP;
   uint32_t* bidx = s_idx + (size_t)warp * CAP;
 
-  float cx = 0.f, cy = 0.f, cz = 0.f, cn = 0.f;
-  if (active) {
-    const float* c = centers + ((size_t)b * G + g) * 3;
-    cx = __ldg(c), cy = __ldg(c + 1), cz = __ldg(c + 2);
-    cn = sqnorm_nofma(cx, cy, cz);
-  }
   int count = 0;
   uint64_t thr = kKeyMax;
   const unsigned lt_mask = (1u << lane) - 1u;
 
   TilePipe pipe;
   pipe.init(tiles, cloud, N, use_bulk);
+  // (the centre is fetched AFTER the first tile has been requested: the two global-memory round trips overlap)
+  float cx = 0.f, cy = 0.f, cz = 0.f, cn = 0.f;
+  if (active) {
+    const float* c = centers + ((size_t)b * G + g) * 3;
+    cx = __ldg(c), cy = __ldg(c + 1), cz = __ldg(c + 2);
+    cn = sqnorm_nofma(cx, cy, cz);
+  }
   const bool masks = use_hist == 1 && pipe.ntiles == 1;   // register-mask selection (single-tile clouds)
   bool from_planes = false;
   for (int t = 0; t < pipe.ntiles; ++t) {
