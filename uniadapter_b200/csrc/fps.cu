@@ -60,6 +60,18 @@ __device__ __forceinline__ void block_argmax(uint32_t bits, uint32_t idx, uint2 
   out_idx = __reduce_min_sync(kFullMask, v.x == bmax ? v.y : 0xffffffffu);
 }
 
+// the same with SIGNED keys (pointnet2 mode of the register kernel: float bit patterns, -1.0f = no candidate)
+__device__ __forceinline__ void block_argmax_signed(int bits, uint32_t idx, uint2 (*s_red)[32], int buf, int lane, int warp,
+                                                    int nwarps, uint32_t& out_idx) {
+  const int wmax = __reduce_max_sync(kFullMask, bits);
+  const uint32_t widx = __reduce_min_sync(kFullMask, bits == wmax ? idx : 0xffffffffu);
+  if (lane == 0) s_red[buf][warp] = make_uint2((uint32_t)wmax, widx);
+  __syncthreads();
+  const uint2 v = lane < nwarps ? s_red[buf][lane] : make_uint2(0x80000000u, 0xffffffffu);
+  const int bmax = __reduce_max_sync(kFullMask, (int)v.x);
+  out_idx = __reduce_min_sync(kFullMask, (int)v.x == bmax ? v.y : 0xffffffffu);
+}
+
 // s_sel holds point indices -- or, in the pointnet2 mode, the tie-order words comp(k), which is also the position of
 // point k in the shared-memory copy of the cloud (no decode on the critical path of the sampling loop)
 template <typename IdxT, bool PN2 = false>
@@ -142,26 +154,20 @@ __global__ void __launch_bounds__(PPT == 12 ? 896 : 1024, 1)
     float best = -1.f;
     if (PN2) {
       uint32_t bestc = 0u;
-      int ties = 0;
 #pragma unroll
       for (int j = 0; j < PPT; ++j) {
         const float d = sqdist_pn2(px[j], py[j], pz[j], cx, cy, cz);
         const float dm = fminf(dmin[j], d);
         dmin[j] = dm;
-        if (dm > best) {
-          best = dm;
-          bestc = cj[j];
-        }
+        // the thread's maximum and, among its points that share it, the lowest tie-order word -- tracked in the scan itself
+        // (a separate tie count + rescan after the loop sat on the serial path of every iteration)
+        const bool gt = dm > best, eq = dm == best;
+        bestc = gt ? cj[j] : (eq ? min(bestc, cj[j]) : bestc);
+        best = gt ? dm : best;
       }
-#pragma unroll
-      for (int j = 0; j < PPT; ++j) ties += dmin[j] == best;
-      if (ties > 1 && best >= 0.f) {     // rare (no vote on the critical path): several of this thread's points share its maximum
-#pragma unroll
-        for (int j = 0; j < PPT; ++j)
-          if (dmin[j] == best) bestc = min(bestc, cj[j]);
-      }
-      block_argmax(pn2_key(best), best < 0.f ? 0u : bestc, s_red, i & 1, lane, warp, nwarps, cur);
-      // nobody has a candidate: every thread reports word 0 = point 0, as upstream
+      // keys are the float bit patterns compared as SIGNED integers: a thread without a candidate holds -1.0f (negative), any
+      // distance (>= 0) beats it, and if nobody has a candidate every thread reports word 0 = point 0, as upstream
+      block_argmax_signed(__float_as_int(best), best < 0.f ? 0u : bestc, s_red, i & 1, lane, warp, nwarps, cur);
     } else {
       int bestj = 0;
 #pragma unroll
@@ -266,23 +272,14 @@ __global__ void __launch_bounds__(512, 1)
     uint32_t bits, cand;           // this thread's candidate: key (distance bits) and tie-order word
     if (PN2) {
       uint32_t bestc = 0u;
-      int ties = 0;
 #pragma unroll
       for (int j = 0; j < PPT; ++j) {
         const float d = sqdist_pn2(px[j], py[j], pz[j], cx, cy, cz);
         const float dm = fminf(dmin[j], d);
         dmin[j] = dm;
-        if (dm > best) {
-          best = dm;
-          bestc = cj[j];
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < PPT; ++j) ties += dmin[j] == best;
-      if (ties > 1 && best >= 0.f) {     // rare: several of this thread's points share its maximum
-#pragma unroll
-        for (int j = 0; j < PPT; ++j)
-          if (dmin[j] == best) bestc = min(bestc, cj[j]);
+        const bool gt = dm > best, eq = dm == best;      // maximum + lowest tie-order word among the points that share it
+        bestc = gt ? cj[j] : (eq ? min(bestc, cj[j]) : bestc);
+        best = gt ? dm : best;
       }
       if (best < 0.f) bestc = 0u;
       bits = pn2_key(best), cand = bestc;
