@@ -153,18 +153,26 @@ __global__ void __launch_bounds__(PPT == 12 ? 896 : 1024, 1)
     const float cx = s_xyz[3 * cur + 0], cy = s_xyz[3 * cur + 1], cz = s_xyz[3 * cur + 2];
     float best = -1.f;
     if (PN2) {
-      uint32_t bestc = 0u;
+      // the thread's maximum and, among its points that share it, the lowest tie-order word: a left-biased pairwise tree
+      // over the thread's points (a sequential scan + tie count + rescan sat on the serial path of every iteration)
+      float td[PPT];
+      uint32_t tc[PPT];
 #pragma unroll
       for (int j = 0; j < PPT; ++j) {
         const float d = sqdist_pn2(px[j], py[j], pz[j], cx, cy, cz);
-        const float dm = fminf(dmin[j], d);
-        dmin[j] = dm;
-        // the thread's maximum and, among its points that share it, the lowest tie-order word -- tracked in the scan itself
-        // (a separate tie count + rescan after the loop sat on the serial path of every iteration)
-        const bool gt = dm > best, eq = dm == best;
-        bestc = gt ? cj[j] : (eq ? min(bestc, cj[j]) : bestc);
-        best = gt ? dm : best;
+        dmin[j] = fminf(dmin[j], d);
+        td[j] = dmin[j], tc[j] = cj[j];
       }
+#pragma unroll
+      for (int st = 1; st < PPT; st *= 2)
+#pragma unroll
+        for (int j = 0; j + st < PPT; j += 2 * st) {
+          const bool gt = td[j + st] > td[j], eq = td[j + st] == td[j];
+          tc[j] = gt ? tc[j + st] : (eq ? min(tc[j], tc[j + st]) : tc[j]);
+          td[j] = gt ? td[j + st] : td[j];
+        }
+      best = td[0];
+      const uint32_t bestc = tc[0];
       // keys are the float bit patterns compared as SIGNED integers: a thread without a candidate holds -1.0f (negative), any
       // distance (>= 0) beats it, and if nobody has a candidate every thread reports word 0 = point 0, as upstream
       block_argmax_signed(__float_as_int(best), best < 0.f ? 0u : bestc, s_red, i & 1, lane, warp, nwarps, cur);
@@ -180,6 +188,8 @@ __global__ void __launch_bounds__(PPT == 12 ? 896 : 1024, 1)
           bestj = j;
         }
       }
+      // (a pairwise tree over the thread's points, as in the pointnet2 branch, was measured here too: no gain at <= 148 clouds,
+      // 3 % slower at 1 184)
       block_argmax(__float_as_uint(best), (uint32_t)(bestj * T + tid), s_red, i & 1, lane, warp, nwarps, cur);
     }
   }
