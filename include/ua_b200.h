@@ -176,7 +176,9 @@ int ua_fuse_logits_f32(const float* clip_logits, const void* dota_logits, int do
  *   scratch: ua_residual_scratch_floats(S,K,M,D) floats, 16-byte aligned.
  * ua_align_loss_grad_f32 evaluates one loss / likelihood matrix [S,K,K] / gradient w.r.t. the residual [S,K,D]
  * (any of them NULL to skip) without touching the residual; out_emb [S,K,D] receives the normalised embeddings.
- * Limits: D % 128 == 0, M in {4,8,12,16}, K <= 128.
+ * Limits: D % 128 == 0, M in {4,8,12,16}, K*K*M < 2^31 (any realistic class count: past K ~ 160 the likelihood matrix is
+ * read from global memory, past K ~ 230 P lives in the scratch too, past K*M = 880 the backward kernel walks the columns in
+ * chunks; the reference's own (K,K,M,D) broadcast is 44 GB at K = 1156).
  * ---------------------------------------------------------------------------------------- */
 long long ua_residual_scratch_floats(int S, int K, int M, int D);
 int ua_residual_learn_f32(const float* text0, long long text0_stream_stride, float* residual, float* adam_m,
