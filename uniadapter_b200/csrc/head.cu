@@ -44,7 +44,8 @@ __global__ void __launch_bounds__(256)
   float* logits = logits_all + (size_t)grp * B * K;
   const float* trow = text + (size_t)(k < K ? k : 0) * D;
   const bool vec = (D & 3) == 0;
-  for (int b0 = 0; b0 < B; b0 += kRowsPerPass) {
+  // blockIdx.z walks the row blocks (a batch of rows meets few classes: 64 rows x 55 classes is 7 x 8 CTAs instead of 7)
+  for (int b0 = blockIdx.z * kRowsPerPass; b0 < B; b0 += gridDim.z * kRowsPerPass) {
     const int nb = min(kRowsPerPass, B - b0);
     __syncthreads();
     for (int i = threadIdx.x; i < nb * D; i += blockDim.x)
@@ -209,7 +210,8 @@ extern "C" int ua_head_f32(const float* x, int B, int D, const float* text, int 
   const size_t smem = (size_t)kRowsPerPass * D * sizeof(float);
   UA_UNSUPPORTED(smem > 200 * 1024, "ua_head_f32: D=%d too large", D);
   if (smem > 48 * 1024) cudaFuncSetAttribute(logits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  dim3 grid((K + W - 1) / W, num_text);
+  const int row_blocks = (B / num_text + kRowsPerPass - 1) / kRowsPerPass;
+  dim3 grid((K + W - 1) / W, num_text, row_blocks < 1 ? 1 : (row_blocks > 256 ? 256 : row_blocks));
   logits_kernel<<<grid, W * 32, smem, st>>>(out_xnorm, B / num_text, D, text, K, scale, out_logits);
   rc = check_launch("ua_head_f32(logits)");
   if (rc != UA_OK) return rc;
