@@ -240,25 +240,44 @@ __global__ void __launch_bounds__(512)
   const int k = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
   for (int d = tid; d < D; d += blockDim.x) s_m[d] = __half2float(__float2half_rn(__ldg(mu + (size_t)k * D + d)));
   __syncthreads();
-  for (int i = warp; i < D; i += W) {
-    const __half* lrow = lam + (size_t)i * D;
-    float acc = 0.f;
-    if ((D & 7) == 0) {
+  if ((D & 7) == 0) {
+    // four rows of Lambda per warp and pass: their 16-byte loads are in flight together and share the eight staged mean
+    // values (one row at a time left one dependent L2 round trip per row on the critical path: 32 of them per warp at
+    // D = 512); the arithmetic of a row is unchanged
+    for (int i0 = warp * 4; i0 < D; i0 += W * 4) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
       for (int jj = lane * 8; jj < D; jj += 256) {
-        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(lrow + jj));
-        const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+        uint4 raw[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float2 f = __half22float2(h2[q]);
-          acc = fmaf(f.x, s_m[jj + 2 * q], acc);
-          acc = fmaf(f.y, s_m[jj + 2 * q + 1], acc);
+        for (int r = 0; r < 4; ++r) raw[r] = __ldg(reinterpret_cast<const uint4*>(lam + (size_t)(i0 + r) * D + jj));
+        float m8[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) m8[q] = s_m[jj + q];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const __half2* h2 = reinterpret_cast<const __half2*>(&raw[r]);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 f = __half22float2(h2[q]);
+            acc[r] = fmaf(f.x, m8[2 * q], acc[r]);
+            acc[r] = fmaf(f.y, m8[2 * q + 1], acc[r]);
+          }
         }
       }
-    } else {
-      for (int jj = lane; jj < D; jj += 32) acc = fmaf(__half2float(lrow[jj]), s_m[jj], acc);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float a = warp_sum(acc[r]);
+        if (lane == 0) s_w[i0 + r] = __half2float(__float2half_rn(a));
+      }
     }
-    acc = warp_sum(acc);
-    if (lane == 0) s_w[i] = __half2float(__float2half_rn(acc));
+  } else {
+    for (int i = warp; i < D; i += W) {
+      const __half* lrow = lam + (size_t)i * D;
+      float acc = 0.f;
+      for (int jj = lane; jj < D; jj += 32) acc = fmaf(__half2float(lrow[jj]), s_m[jj], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) s_w[i] = __half2float(__float2half_rn(acc));
+    }
   }
   __syncthreads();
   // c = 0.5 * sum_i half(M_i * W_i)   (sum accumulated in fp32, rounded to half, then halved in half)
