@@ -49,3 +49,29 @@ def test_no_cpu_fallback():
         ua.fps_sample(torch.zeros(1, 16, 3), 4)
     with pytest.raises(ua._lib.UaError):
         ua.zero_shot_head(torch.zeros(1, 8), torch.zeros(3, 8))
+
+
+def test_residual_learning_plans_for_any_class_count(libpath):
+    """Host logic only (no launch): the scratch planner of ua_residual_learn_f32 accepts the class counts of every BASELINE
+    data set -- ModelNet40 / ScanObjectNN / ShapeNet-C, OmniObject3D's 216 (likelihood matrix out of shared memory,
+    column-chunked backward) and Objaverse-LVIS's 1156 (P in the scratch too: its K*K floats show up in the plan) -- and
+    still refuses the shapes it cannot tile."""
+    from uniadapter_b200 import _lib
+    f = _lib.lib().ua_residual_scratch_floats
+    small = f(1, 40, 8, 512)
+    assert small > 0
+    assert f(15, 40, 8, 512) > small
+    assert f(1, 216, 8, 512) > 0
+    lvis = f(1, 1156, 8, 1024)
+    assert lvis >= 1156 * 1156 * (8 + 2) + 1156 * 8 * 1024      # Wt + LM + P (global) + 1/v
+    assert f(1, 40, 8, 520) == -1          # D % 128 != 0
+    assert f(1, 40, 6, 512) == -1          # M not a multiple of 4
+
+
+def test_tuning_knobs_are_validated(libpath):
+    from uniadapter_b200 import _lib
+    for key in ("knn_hist", "dota_ka", "dota_pdl", "sample_per", "sample_v", "fps_cluster"):
+        _lib.set_tuning(key, 0)
+    _lib.set_tuning("dota_pdl", 1)
+    with pytest.raises(_lib.UaError):
+        _lib.set_tuning("no_such_knob", 1)
