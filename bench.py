@@ -238,7 +238,9 @@ def cache_step_roofline(dev, flush, S, K, M, D, label):
     dst_t = torch.empty_like(src_t)
     copy_us = median_us(lambda: dst_t.copy_(src_t), flush)
     r = hbm_roofline("ua_modedota_sample_step_f32 (modedota_sample_kernel): predict + fit + fit, one pass", label, unit,
-                     single, peak, src, traffic_key="modedota_sample_kernel_lvis" if K >= 1000 else None,
+                     single, peak, src,
+                     traffic_key="modedota_sample_kernel_lvis" if K >= 1000 else
+                     ("modedota_sample_kernel_cfg2" if (S, K, M, D) == (15, 40, 8, 512) else None),
                      accounting="achieved / frac: SURVEY 8d's algorithmic bytes of a sample step (32*S*K*M*D: predict fused "
                                 "into fit #1, two fits, state in + out per fit) over the time of the ONE launch that does the "
                                 "whole sample step; the single pass moves half of them (moved_bytes_per_launch), the fraction "

@@ -67,6 +67,18 @@ xb = torch.nn.functional.normalize(torch.randn(Bb, D, device=dev), dim=-1)
 gb = torch.softmax(100 * xb @ tb.t(), 1)
 for _ in range(ROUNDS):
     cold(); mb.predict_then_fit(xb, xb, gb)
+# cfg 2 cache step: 15 streams x 40 classes, M = 8, D = 512 (the kernel bench.py's headline roofline line quotes)
+from uniadapter_b200.engine import MultiStreamModeDota
+from uniadapter_b200.streams import synthetic_text_features
+t2 = synthetic_text_features(40, 512, seed=1).to(dev)
+c2 = MultiStreamModeDota(cfg, 512, 40, t2, 8, 15, dev)
+x2 = torch.nn.functional.normalize(torch.randn(15, 512, device=dev), dim=-1)
+xa2 = torch.nn.functional.normalize(x2 + 0.01 * torch.randn(15, 512, device=dev), dim=-1)
+g2 = torch.softmax(100 * x2 @ t2.t(), 1).contiguous()
+o2 = torch.zeros(15, 40, device=dev)
+c2.sample_step(x2, xa2, g2, o2)
+for _ in range(ROUNDS):
+    cold(); c2.sample_step(x2, xa2, g2, o2)
 # cfg 5 zero-shot head at batch 64 on the tcgen05 GEMM (HeadPlan: prepare + 3xTF32 GEMM + row statistics), K = 55 and 1156
 xh = torch.randn(64, D, device=dev)
 for Kh in (55, 1156):
