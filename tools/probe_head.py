@@ -5,12 +5,11 @@ import torch
 import uniadapter_b200 as ua
 from uniadapter_b200.head import HeadPlan
 from bench import L2Flush, median_us
-from oracle import synth
 dev = torch.device("cuda:0")
 flush = L2Flush(dev)
 D = 1024
 for K in (55, 216, 1156):
-    text = torch.from_numpy(synth.unit_rows(K, D, K)).to(dev)
+    text = torch.nn.functional.normalize(torch.randn(K, D, generator=torch.Generator().manual_seed(K)), dim=-1).to(dev)
     plan = HeadPlan(text)
     for B in (8, 64, 256, 1024):
         x = torch.randn(B, D, device=dev)
